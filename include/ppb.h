@@ -1,0 +1,146 @@
+/*
+ * ppb.h — C ABI of the B200-native core/accessory sketch-distance engine (libppb.so).
+ *
+ * This is the drop-in boundary for ONE path of bacpop/PopPUNK: the all-vs-all and
+ * query-vs-ref (core pi, accessory a) distance calculation that PopPUNK reaches through
+ *     PopPUNK/sketchlib.py:475-632   queryDatabase()
+ *         -> pp_sketchlib.queryDatabase(ref_db_name, query_db_name, rList, qList, klist,
+ *                random_correct, jaccard, num_threads, use_gpu, device_id)
+ *            (call sites PopPUNK/sketchlib.py:528-537, 547-564, 584-593, 601-618;
+ *             positional order pinned by test/test-update-gpu.py:85-86)
+ * and the step immediately after it,
+ *     src/boundary.cpp:42-80         line_dist() / assign_threshold()
+ *            (bound at src/python_bindings.cpp:18-25, 79-83; called models.py:1085-1089).
+ *
+ * Everything here is plain C: pointers, sizes, scalars.  No torch / pybind / Eigen types.
+ * Functions never throw and never allocate caller-visible output; every output buffer is owned
+ * by the caller.  Return value: 0 = ok, nonzero = error code (message via ppb_last_error()).
+ *
+ * ---- data conventions -------------------------------------------------------------------
+ * Sketch (reference type: HDF5 dataset /sketches/<name>/<k>, schema PopPUNK/web.py:14-61;
+ * fixture test/json_sketch.txt: sketchsize64=156, bbits=14, 2184 = 156*14 words per k):
+ *   one genome, one k  = W = sketchsize64 * bbits  uint64 words, bindash bit-sliced:
+ *   word [s*bbits + b] holds bit b of the bbits-bit signatures of bins 64s .. 64s+63.
+ *   A "sketch array" is  uint64 [n][K][W]  row-major (genome-major, then k in klist order).
+ *   bbits must be 14 (the only value pp-sketchlib writes).
+ * Output row order (reference: PopPUNK/utils.py:199-226, src/boundary.cpp:22-37,97-123):
+ *   self  (qry == NULL): condensed upper triangle, row(i<j) = n*i - i*(i+1)/2 + j - 1 - i
+ *   non-self            : query-major rectangle,   row(q,r) = q*n_ref + r
+ *   [row_begin,row_end) selects a contiguous shard of rows; out holds row_end-row_begin rows.
+ * Random-match table (pp_sketchlib random_correct=True, sketchlib.py:533,589):
+ *   rand_table float32 [n_clusters][n_clusters][K], entry (ref_cluster, qry_cluster, k);
+ *   cluster ids uint16 per genome.  rand_table == NULL  <=>  random_correct=False.
+ */
+#ifndef PPB_H
+#define PPB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPB_VERSION 100          /* 0.1.0 */
+#define PPB_BBITS 14             /* signature bits per bin (pp-sketchlib constant) */
+#define PPB_MAX_K 32             /* max number of k-mer lengths in one call */
+#define PPB_MIN_JACCARD_BINS 5   /* J < 5/S ends the regression series (docs/sketching.rst:161-165) */
+
+/* output modes: what one output row holds */
+#define PPB_OUT_DISTS   0        /* float32 [2]  (core, accessory)   jaccard=False */
+#define PPB_OUT_JACCARD 1        /* float32 [K]  per-k Jaccard        jaccard=True  */
+#define PPB_OUT_COUNTS  2        /* uint32  [K]  per-k matching-bin counts c_k (bit-exact probe) */
+
+/* error codes */
+#define PPB_OK            0
+#define PPB_ERR_ARG       1
+#define PPB_ERR_CUDA      2
+#define PPB_ERR_NO_DEVICE 3
+#define PPB_ERR_NOMEM     4
+
+/* Decision boundary for the fused assign_threshold epilogue.
+ * Replaces models.py:1085-1089 `assignThreshold(X/self.scale, slope, x_max, y_max)`:
+ * x0 = core/scale_x, y0 = acc/scale_y (float32 division), then src/boundary.cpp:42-58. */
+typedef struct ppb_boundary {
+    int32_t slope;               /* 0 vertical, 1 horizontal, 2 sloped (boundary.cpp:45-55) */
+    float   x_max, y_max;        /* narrowed double->float as in python_bindings.cpp:19-23 */
+    float   scale_x, scale_y;    /* 1.0f for none */
+} ppb_boundary;
+
+int         ppb_version(void);
+const char *ppb_last_error(void);
+/* number of visible CUDA devices; <0 on error. */
+int         ppb_device_count(void);
+
+/* ---------------- index maps (src/boundary.cpp:18-37; utils.py:199-261) ---------------- */
+int64_t ppb_square_to_condensed(int64_t i, int64_t j, int64_t n);
+int64_t ppb_calc_row_idx(int64_t k, int64_t n);
+int64_t ppb_calc_col_idx(int64_t k, int64_t i, int64_t n);
+int64_t ppb_num_rows(int64_t n_ref, int64_t n_qry, int self);
+
+/* ---------------- device-pointer entry points (caller owns all device memory) -----------
+ * stream is a cudaStream_t passed as void*. All work is enqueued on it; no host sync unless
+ * stated. Pointers are device pointers (torch tensor.data_ptr()).                           */
+
+/* Size in bytes of the packed (lane-sliced) sketch buffer for n genomes. */
+size_t ppb_packed_bytes(int64_t n, int32_t K, int32_t sketchsize64);
+
+/* Re-lay a canonical sketch array uint64 [n_src][K][W] into the engine's packed layout.
+ * idx (device int64 [n], may be NULL = identity with n == n_src) gathers genomes into list
+ * order — the rList/qList subset+order semantics of pp_sketchlib.queryDatabase.             */
+int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, int64_t n,
+                 int32_t K, int32_t sketchsize64, uint32_t *d_packed, void *stream);
+
+/* The hot path.  Replaces pp_sketchlib.queryDatabase(...) after the sketches are on the device.
+ *   d_qry_packed == NULL  => self mode (n_qry ignored)
+ *   kmers        host int32 [K], ascending k-mer lengths (x of the regression)
+ *   d_rand_table device float32 [C][C][K] or NULL; d_ref_cluster/d_qry_cluster device uint16
+ *   out_mode     PPB_OUT_*; d_out device buffer of (row_end-row_begin) rows of that mode,
+ *                may be NULL when only labels are wanted (PPB_OUT_DISTS only)
+ *   boundary/d_labels  optional fused assign_threshold: int8 label in {-1,0,+1} per row
+ *   d_n_degenerate     optional device counter (uint64), incremented once per row whose
+ *                      series has < 2 usable k (row gets (0,0)); caller zeroes it.           */
+int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref,
+                  const uint32_t *d_qry_packed, int64_t n_qry,
+                  const int32_t *kmers, int32_t K, int32_t sketchsize64,
+                  const float *d_rand_table, int32_t n_clusters,
+                  const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                  int64_t row_begin, int64_t row_end,
+                  int32_t out_mode, void *d_out,
+                  const ppb_boundary *boundary, int8_t *d_labels,
+                  unsigned long long *d_n_degenerate, void *stream);
+
+/* Standalone assign_threshold over an existing (n,2) float32 row-major array
+ * (src/boundary.cpp:60-80). d_out float32 [n] in {-1,0,+1}.                                  */
+int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope,
+                             float x_max, float y_max, float *d_out, void *stream);
+
+/* ---------------- host-buffer entry points (what a pybind/ctypes shim of PopPUNK calls) --
+ * Same semantics as above with HOST pointers: the library stages host->device copies,
+ * packs, runs the kernels in row chunks and copies results back, overlapping copy and
+ * compute on internal streams.  Blocking.  out may be pinned or pageable.                    */
+int ppb_query_host(const uint64_t *ref, int64_t n_ref,
+                   const uint64_t *qry, int64_t n_qry,
+                   const int32_t *kmers, int32_t K, int32_t sketchsize64, int32_t bbits,
+                   const float *rand_table, int32_t n_clusters,
+                   const uint16_t *ref_cluster, const uint16_t *qry_cluster,
+                   int64_t row_begin, int64_t row_end,
+                   int32_t out_mode, void *out,
+                   const ppb_boundary *boundary, int8_t *labels,
+                   int64_t *n_degenerate, int32_t device_id);
+
+int ppb_assign_threshold_host(const float *dists, int64_t n, int32_t slope,
+                              float x_max, float y_max, float *out, int32_t device_id);
+
+/* ---------------- measurement helpers ---------------------------------------------------
+ * Integer-pipe micro-roofline: runs a LOP3-only (mode 0), POPC-only (mode 1) or
+ * LOP3+POPC mixed (mode 2) kernel on `stream` and returns lane-ops executed; caller times it. */
+int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *lane_ops, void *stream);
+
+/* kernel launch counter since library load (for bench.py's gpu_launches). */
+int64_t ppb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPB_H */

@@ -1,0 +1,261 @@
+"""CPU ORACLE — Python face.  TEST INFRASTRUCTURE ONLY (see the header of ppb_oracle.c).
+
+Two independent restatements of the reference algorithm for the distance hot path:
+
+* :func:`query` & co — ctypes bindings of ``libppo.so`` (``ppb_oracle.c``, C + OpenMP), the checker
+  used at sizes up to ~10^8 pairs and the CPU baseline timed by ``bench.py``;
+* :func:`counts_numpy`, :func:`regress_numpy`, :func:`assign_threshold_numpy` — NumPy restatements
+  written a *different way* (un-sliced signature equality instead of bit-sliced popcounts;
+  ``numpy.linalg.lstsq`` instead of closed-form OLS) that pin the C oracle in ``tests/``.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this module.
+PARITY STATUS: parity unpinned for (pi, a) values — pp-sketchlib is absent (details in ppb_oracle.c).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DISTS, OUT_JACCARD, OUT_COUNTS = 0, 1, 2
+BBITS = 14
+
+
+class Boundary(C.Structure):
+    _fields_ = [("slope", C.c_int32), ("x_max", C.c_float), ("y_max", C.c_float),
+                ("scale_x", C.c_float), ("scale_y", C.c_float)]
+
+
+def build(native: bool = False) -> str:
+    """Compile the C oracle (``make -C oracle``); returns the path of the shared object."""
+    target = ["native"] if native else []
+    subprocess.run(["make", "-s", "-C", _HERE] + target, check=True)
+    return os.path.join(_HERE, "libppo_native.so" if native else "libppo.so")
+
+
+_lib = None
+
+
+def lib(native: bool = False):
+    global _lib
+    if _lib is not None and not native:
+        return _lib
+    path = os.path.join(_HERE, "libppo_native.so" if native else "libppo.so")
+    if not os.path.exists(path):
+        build(native)
+    L = C.CDLL(path)
+    i64, i32, vp = C.c_int64, C.c_int32, C.c_void_p
+    L.ppo_query_host.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp, vp, i64, i64,
+                                 i32, vp, vp, vp, vp, i32]
+    L.ppo_query_host.restype = C.c_int
+    L.ppo_assign_threshold.argtypes = [vp, i64, i32, C.c_float, C.c_float, vp, i32]
+    L.ppo_assign_threshold.restype = C.c_int
+    for name in ("ppo_square_to_condensed",):
+        getattr(L, name).argtypes = [i64, i64, i64]
+        getattr(L, name).restype = i64
+    L.ppo_calc_row_idx.argtypes = [i64, i64]
+    L.ppo_calc_row_idx.restype = i64
+    L.ppo_calc_col_idx.argtypes = [i64, i64, i64]
+    L.ppo_calc_col_idx.restype = i64
+    L.ppo_num_rows.argtypes = [i64, i64, C.c_int]
+    L.ppo_num_rows.restype = i64
+    L.ppo_max_threads.restype = C.c_int
+    L.ppo_regress_rows.argtypes = [vp, i64, vp, i32, C.c_double, vp]
+    L.ppo_regress_rows.restype = i64
+    if not native:
+        _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def max_threads() -> int:
+    return int(lib().ppo_max_threads())
+
+
+def num_rows(n_ref, n_qry=None):
+    return n_ref * (n_ref - 1) // 2 if n_qry is None else n_ref * n_qry
+
+
+def query(ref, qry, kmers, rand_table=None, ref_cluster=None, qry_cluster=None,
+          row_begin=0, row_end=None, out_mode=OUT_DISTS, boundary=None, threads=None,
+          native=False):
+    """Oracle twin of ``ppb_query_host``.  ``ref``/``qry``: uint64 ``[n][K][W]``; qry=None => self.
+
+    Returns ``(out, n_degenerate)`` or ``(out, labels, n_degenerate)`` when ``boundary`` is given
+    (tuple ``(slope, x_max, y_max, scale_x, scale_y)``).
+    """
+    L = lib(native)
+    ref = np.ascontiguousarray(ref, dtype=np.uint64)
+    n_ref, K, W = ref.shape
+    if W % BBITS:
+        raise ValueError("W must be sketchsize64*14")
+    ss64 = W // BBITS
+    n_qry = 0
+    if qry is not None:
+        qry = np.ascontiguousarray(qry, dtype=np.uint64)
+        n_qry = qry.shape[0]
+        assert qry.shape[1:] == ref.shape[1:]
+    kmers = np.ascontiguousarray(kmers, dtype=np.int32)
+    assert kmers.shape == (K,)
+    total = num_rows(n_ref, None if qry is None else n_qry)
+    if row_end is None:
+        row_end = total
+    rows = row_end - row_begin
+    nclus = 0
+    if rand_table is not None:
+        rand_table = np.ascontiguousarray(rand_table, dtype=np.float32)
+        nclus = rand_table.shape[0]
+        assert rand_table.shape == (nclus, nclus, K)
+        ref_cluster = np.ascontiguousarray(ref_cluster, dtype=np.uint16)
+        if qry is not None:
+            qry_cluster = np.ascontiguousarray(qry_cluster, dtype=np.uint16)
+    if out_mode == OUT_DISTS:
+        out = np.empty((rows, 2), dtype=np.float32)
+    elif out_mode == OUT_JACCARD:
+        out = np.empty((rows, K), dtype=np.float32)
+    else:
+        out = np.empty((rows, K), dtype=np.uint32)
+    labels = None
+    bnd = None
+    if boundary is not None:
+        bnd = Boundary(*boundary)
+        labels = np.empty(rows, dtype=np.int8)
+    ndeg = C.c_int64(0)
+    if threads is None:
+        threads = max_threads()
+    rc = L.ppo_query_host(_ptr(ref), n_ref, _ptr(qry), n_qry, _ptr(kmers), K, ss64, BBITS,
+                          _ptr(rand_table), nclus, _ptr(ref_cluster), _ptr(qry_cluster),
+                          row_begin, row_end, out_mode, _ptr(out),
+                          C.byref(bnd) if bnd is not None else None, _ptr(labels),
+                          C.byref(ndeg), threads)
+    if rc != 0:
+        raise RuntimeError(f"ppo_query_host failed with code {rc}")
+    if boundary is not None:
+        return out, labels, int(ndeg.value)
+    return out, int(ndeg.value)
+
+
+def assign_threshold(dists, slope, x_max, y_max, threads=1):
+    """Oracle twin of ``poppunk_refine.assignThreshold`` (src/boundary.cpp:60-80)."""
+    d = np.ascontiguousarray(dists, dtype=np.float32)
+    out = np.empty(d.shape[0], dtype=np.float32)
+    rc = lib().ppo_assign_threshold(_ptr(d), d.shape[0], slope, x_max, y_max, _ptr(out), threads)
+    if rc != 0:
+        raise RuntimeError("ppo_assign_threshold failed")
+    return out
+
+
+def regress_rows(jac, kmers, S):
+    """(core, acc) float32 [rows][2] from per-k Jaccards float64 [rows][K] (C oracle regression only)."""
+    jac = np.ascontiguousarray(jac, dtype=np.float64)
+    kmers = np.ascontiguousarray(kmers, dtype=np.int32)
+    out = np.empty((jac.shape[0], 2), dtype=np.float32)
+    deg = lib().ppo_regress_rows(_ptr(jac), jac.shape[0], _ptr(kmers), jac.shape[1], float(S), _ptr(out))
+    return out, int(deg)
+
+
+def square_to_condensed(i, j, n):
+    return int(lib().ppo_square_to_condensed(i, j, n))
+
+
+def calc_row_idx(k, n):
+    return int(lib().ppo_calc_row_idx(k, n))
+
+
+def calc_col_idx(k, i, n):
+    return int(lib().ppo_calc_col_idx(k, i, n))
+
+
+# --------------------------------------------------------------------------------------------
+# NumPy restatements (small cases; a different formulation from the C code on purpose)
+# --------------------------------------------------------------------------------------------
+def _unslice(words, ss64):
+    words = np.ascontiguousarray(words, dtype="<u8")
+    lead = words.shape[:-1]
+    w = words.reshape(lead + (ss64, BBITS))
+    sig = np.zeros(lead + (ss64, 64), dtype=np.uint16)
+    for b in range(BBITS):
+        plane = np.ascontiguousarray(w[..., b]).view(np.uint8).reshape(lead + (ss64, 8))
+        sig |= np.unpackbits(plane, axis=-1, bitorder="little").astype(np.uint16) << np.uint16(b)
+    return sig.reshape(lead + (ss64 * 64,))
+
+
+def pair_rows(n_ref, n_qry=None):
+    """(i, j) index arrays in output row order (utils.py:199-226): self -> i<j row-major;
+    non-self -> i = query (slow), j = ref (fast)."""
+    if n_qry is None:
+        i, j = np.triu_indices(n_ref, k=1)
+        return i, j
+    q, r = np.divmod(np.arange(n_ref * n_qry), n_ref)
+    return q, r
+
+
+def counts_numpy(ref, qry=None):
+    """c_k = number of bins whose 14-bit signatures are equal — the b-bit MinHash definition
+    (BinDash, citation.py:35-38), computed on UN-sliced signatures."""
+    ss64 = ref.shape[-1] // BBITS
+    sr = _unslice(ref, ss64)
+    i, j = pair_rows(ref.shape[0], None if qry is None else qry.shape[0])
+    sa = sr if qry is None else _unslice(qry, ss64)
+    out = np.empty((len(i), ref.shape[1]), dtype=np.uint32)
+    step = 4096
+    for s in range(0, len(i), step):
+        out[s:s + step] = (sa[i[s:s + step]] == sr[j[s:s + step]]).sum(axis=-1)
+    return out
+
+
+def regress_numpy(jac, kmers, S):
+    """(core, acc) per row from per-k Jaccards via numpy.linalg.lstsq on [1, k] (the design matrix
+    of PopPUNK/sketchlib.py:541,652-660), with the < 5/S truncation and the <= 0 clamps."""
+    jac = np.asarray(jac, dtype=np.float64)
+    kmers = np.asarray(kmers, dtype=np.float64)
+    out = np.zeros((jac.shape[0], 2), dtype=np.float32)
+    ndeg = 0
+    tol = 5.0 / S
+    for r in range(jac.shape[0]):
+        below = np.nonzero(jac[r] < tol)[0]
+        n = below[0] if len(below) else len(kmers)
+        if n < 2:
+            ndeg += 1
+            continue
+        X = np.stack([np.ones(n), kmers[:n]], axis=1)
+        (alpha, beta), *_ = np.linalg.lstsq(X, np.log(jac[r, :n]), rcond=None)
+        out[r, 0] = 1.0 - np.exp(beta) if beta < 0 else 0.0
+        out[r, 1] = 1.0 - np.exp(alpha) if alpha < 0 else 0.0
+    return out, ndeg
+
+
+def jaccard_numpy(counts, S, rand_table=None, ref_cluster=None, qry_cluster=None, n_ref=None,
+                  n_qry=None):
+    counts = np.asarray(counts, dtype=np.float64)
+    jobs = counts / S
+    if rand_table is None:
+        return jobs
+    i, j = pair_rows(n_ref, n_qry)
+    cq = (ref_cluster if n_qry is None else qry_cluster)[i]
+    cr = ref_cluster[j]
+    r = rand_table.astype(np.float64)[cr, cq]  # [rows][K]
+    return np.maximum(jobs - r, 0.0) / (1.0 - r)
+
+
+def assign_threshold_numpy(dists, slope, x_max, y_max):
+    """float32 restatement of src/boundary.cpp:42-80 (each op rounded to float32, no FMA)."""
+    d = np.asarray(dists, dtype=np.float32)
+    x0, y0 = d[:, 0], d[:, 1]
+    xm, ym = np.float32(x_max), np.float32(y_max)
+    if slope == 2:
+        if xm == 0 or ym == 0:
+            s = np.sqrt((x0 * x0 + y0 * y0).astype(np.float32)).astype(np.float32)
+        else:
+            s = ((y0 * xm).astype(np.float32) + (x0 * ym).astype(np.float32)).astype(np.float32) - np.float32(xm * ym)
+    elif slope == 0:
+        s = x0 - xm
+    else:
+        s = y0 - ym
+    return np.sign(s).astype(np.float32)

@@ -1,0 +1,118 @@
+"""Seeded synthetic sketch generator (bit-sliced bindash sketches without a sketcher).
+
+The reference obtains sketches from ``pp_sketchlib.constructDatabase`` (PopPUNK/sketchlib.py:410-422),
+which is outside the hot path.  For parity tests and bench.py we need
+sketch arrays with realistic, non-degenerate Jaccards: pure i.i.d. random signatures give
+J ~ 2^-14 < 5/S for every pair, i.e. every regression is truncated away (docs/sketching.rst:161-165).
+
+Model: a root signature table, ``n_lineages`` lineage tables derived from it and
+genomes derived from a lineage.  At each derivation step and for each k a bin keeps its parent's
+signature with probability ``p_k = sqrt((1-a)(1-pi)^k)`` and is redrawn uniformly otherwise, so two
+genomes with a common parent have ``E[J_k] ~ (1-a)(1-pi)^k`` — the relation PopPUNK fits
+(PopPUNK/sketchlib.py:482).
+
+Layout produced (the reference's HDF5 dataset layout, PopPUNK/web.py:14-61 and
+test/json_sketch.txt): ``uint64 [n][K][W]``, ``W = sketchsize64 * 14``, word ``s*14 + b`` = bit ``b``
+of the 14-bit signatures of bins ``64 s .. 64 s + 63`` (bin = bit position).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BBITS = 14
+
+
+def bitslice(sig: np.ndarray) -> np.ndarray:
+    """uint16 signatures ``[..., S]`` (values < 2**14) -> bit-sliced uint64 ``[..., S//64 * 14]``."""
+    sig = np.ascontiguousarray(sig, dtype=np.uint16)
+    S = sig.shape[-1]
+    if S % 64:
+        raise ValueError("number of bins must be a multiple of 64")
+    lead = sig.shape[:-1]
+    s64 = S // 64
+    out = np.empty(lead + (s64, BBITS), dtype=np.uint64)
+    blk = sig.reshape(lead + (s64, 64))
+    for b in range(BBITS):
+        bits = ((blk >> np.uint16(b)) & np.uint16(1)).astype(np.uint8)
+        packed = np.packbits(bits, axis=-1, bitorder="little")  # 8 bytes, bin t -> bit t
+        out[..., b] = np.ascontiguousarray(packed).view("<u8").reshape(lead + (s64,))
+    return out.reshape(lead + (s64 * BBITS,))
+
+
+def unslice(words: np.ndarray, sketchsize64: int) -> np.ndarray:
+    """Inverse of :func:`bitslice`: uint64 ``[..., W]`` -> uint16 signatures ``[..., 64*sketchsize64]``."""
+    words = np.ascontiguousarray(words, dtype="<u8")
+    lead = words.shape[:-1]
+    w = words.reshape(lead + (sketchsize64, BBITS))
+    sig = np.zeros(lead + (sketchsize64, 64), dtype=np.uint16)
+    for b in range(BBITS):
+        plane = np.ascontiguousarray(w[..., b]).view(np.uint8).reshape(lead + (sketchsize64, 8))
+        bits = np.unpackbits(plane, axis=-1, bitorder="little").astype(np.uint16)
+        sig |= bits << np.uint16(b)
+    return sig.reshape(lead + (sketchsize64 * 64,))
+
+
+def _derive(rng, parent, p_keep):
+    """Keep each parent bin with probability p_keep[k] (broadcast over bins), else redraw."""
+    keep = rng.random(parent.shape, dtype=np.float32) < p_keep[..., None].astype(np.float32)
+    fresh = rng.integers(0, 1 << BBITS, size=parent.shape, dtype=np.uint16)
+    return np.where(keep, parent, fresh)
+
+
+def synth_signatures(n, kmers, sketchsize64, seed=42, n_lineages=8,
+                     pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=2048, sample_seed=0):
+    """Generator of ``(start, uint16 [m][K][S])`` signature chunks for ``n`` genomes.
+
+    ``seed`` fixes the population (root + lineages); ``sample_seed`` fixes the genomes drawn from it, so
+    a query set (``sample_seed=1``) is related to a reference set (``sample_seed=0``) of the same ``seed``.
+    """
+    kmers = np.asarray(kmers, dtype=np.float64)
+    K = len(kmers)
+    S = 64 * sketchsize64
+    rng = np.random.default_rng(seed)
+    root = rng.integers(0, 1 << BBITS, size=(K, S), dtype=np.uint16)
+
+    def p_keep(m):
+        pi = rng.uniform(*pi_range, size=m)
+        a = rng.uniform(*a_range, size=m)
+        return np.sqrt((1.0 - a)[:, None] * (1.0 - pi)[:, None] ** kmers[None, :])  # [m][K]
+
+    lin = _derive(rng, np.broadcast_to(root, (n_lineages, K, S)), p_keep(n_lineages))
+    rng = np.random.default_rng([seed, sample_seed])
+    for start in range(0, n, chunk):
+        m = min(chunk, n - start)
+        which = rng.integers(0, n_lineages, size=m)
+        yield start, _derive(rng, lin[which], p_keep(m))
+
+
+def synth_sketches(n, kmers, sketchsize64, seed=42, **kw) -> np.ndarray:
+    """Bit-sliced synthetic sketch array ``uint64 [n][K][W]`` (host, NumPy)."""
+    K = len(kmers)
+    out = np.empty((n, K, sketchsize64 * BBITS), dtype=np.uint64)
+    for start, sig in synth_signatures(n, kmers, sketchsize64, seed=seed, **kw):
+        out[start:start + sig.shape[0]] = bitslice(sig)
+    return out
+
+
+def random_match_table(kmers, n_clusters=3, genome_length=2.1e6, seed=42):
+    """A small random-match table shaped like pp-sketchlib's RandomMC output.
+
+    ``r = 1 - (1 - 2*4^-k)^(-l)``... the docs' formula (docs/sketching.rst:107-118) is written with a
+    sign slip; the chance that a given k-mer occurs in a random genome of length ``l`` is
+    ``r = 1 - (1 - 4^-k)^(2 l)`` (both strands) and ``J_r = r^2 / (2 r - r^2)``.  Clusters get slightly
+    different effective lengths so the table is not constant.  Returns float32 ``[C][C][K]`` symmetric.
+    """
+    kmers = np.asarray(kmers, dtype=np.float64)
+    rng = np.random.default_rng(seed)
+    lengths = genome_length * rng.uniform(0.8, 1.25, size=n_clusters)
+    r = -np.expm1(2.0 * lengths[:, None] * np.log1p(-(4.0 ** (-kmers[None, :]))))  # [C][K]
+    r1 = r[:, None, :]
+    r2 = r[None, :, :]
+    den = r1 + r2 - r1 * r2
+    jr = np.where(den > 0, (r1 * r2) / np.where(den > 0, den, 1.0), 0.0)
+    return np.ascontiguousarray(jr, dtype=np.float32)
+
+
+def synth_clusters(n, n_clusters=3, seed=42) -> np.ndarray:
+    rng = np.random.default_rng(seed + 1)
+    return rng.integers(0, n_clusters, size=n).astype(np.uint16)

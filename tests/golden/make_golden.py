@@ -1,0 +1,105 @@
+"""Generate the committed golden fixtures from the reference tree (run HERE, where /root/reference exists).
+
+    python tests/golden/make_golden.py [/root/reference]
+
+Nothing under tests/ reads /root/reference at run time; only this script does.  It copies no reference
+source into the repo: reference *functions* are extracted with ``ast`` and executed in memory, and only
+their numeric outputs are saved.
+
+Fixtures written next to this file:
+  json_sketch.npz      the reference's only real pp-sketchlib sketch (test/json_sketch.txt): pins the
+                       sketch schema W = sketchsize64*bbits, bbits = 14
+  refine_grid.npz      test/test-refine.py:46-61 — 10x10 float32 grid, boundary (0.5, 0.5), slopes 0/1/2,
+                       labels from the reference's own ``withinBoundary`` restatement (:10-23)
+  fit_kmer_curve.npz   PopPUNK/sketchlib.py:635-670 ``fitKmerCurve`` (scipy bounded least squares) run on
+                       seeded per-k Jaccard vectors: pins model, clamp and (core, acc) output order
+"""
+import ast
+import json
+import os
+import sys
+
+import numpy as np
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def extract_function(path, name, env):
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), env)
+            return env[name]
+    raise KeyError(name)
+
+
+def json_sketch():
+    d = json.load(open(os.path.join(REF, "test", "json_sketch.txt")))
+    kmers = sorted(int(k) for k in d if k.isdigit())
+    sk = np.stack([np.array(d[str(k)], dtype=np.uint64) for k in kmers])
+    np.savez_compressed(os.path.join(HERE, "json_sketch.npz"), kmers=np.array(kmers, dtype=np.int32),
+                        sketch=sk, sketchsize64=np.int32(d["sketchsize64"]), bbits=np.int32(d["bbits"]),
+                        length=np.int64(d["length"]), bases=np.array(d["bases"], dtype=np.float64))
+    print("json_sketch:", kmers, sk.shape, d["sketchsize64"], d["bbits"])
+
+
+def refine_grid():
+    within = extract_function(os.path.join(REF, "test", "test-refine.py"), "withinBoundary", {"np": np})
+    x = np.arange(0, 1, 0.1, dtype=np.float32)
+    y = np.arange(0, 1, 0.1, dtype=np.float32)
+    xv, yv = np.meshgrid(x, y)
+    dist = np.hstack((xv.reshape(-1, 1), yv.reshape(-1, 1)))
+    labels = np.stack([within(dist, 0.5, 0.5, s) for s in (0, 1, 2)]).astype(np.float32)
+    # a seeded random cloud like test-refine.py:64-66 (the reference's is unseeded)
+    rng = np.random.default_rng(7)
+    cloud = rng.random((4950, 2)).astype(np.float32)
+    cloud_labels = np.stack([within(cloud, 0.5, 0.5, s) for s in (0, 1, 2)]).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "refine_grid.npz"), dist=dist, labels=labels, cloud=cloud,
+                        cloud_labels=cloud_labels, x_max=np.float32(0.5), y_max=np.float32(0.5))
+    print("refine_grid:", dist.shape, labels.shape, [int((l == -1).sum()) for l in labels])
+
+
+def fit_kmer_curve():
+    from scipy import optimize
+    fit = extract_function(os.path.join(REF, "PopPUNK", "sketchlib.py"), "fitKmerCurve",
+                           {"np": np, "optimize": optimize, "sys": sys})
+    rng = np.random.default_rng(11)
+    klists = [np.arange(13, 30, 4), np.array([15, 19, 23, 27, 31]), np.arange(13, 30, 3), np.arange(14, 30, 3)]
+    rows = []
+    for klist in klists:
+        jacobian = -np.hstack((np.ones((klist.shape[0], 1)), klist.reshape(-1, 1)))
+        for rep in range(60):
+            if rep < 40:
+                core = rng.uniform(0.0005, 0.05)
+                acc = rng.uniform(0.005, 0.5)
+            else:  # near-identical genomes: sketch noise pushes slope/intercept to the <= 0 bounds
+                core = rng.uniform(0.0, 0.0003)
+                acc = rng.uniform(0.0, 0.003)
+            S = 1024
+            # binomial sketch noise so that some fits hit the <= 0 clamps
+            jac = rng.binomial(S, (1 - acc) * (1 - core) ** klist) / S
+            if (jac <= 0).any():
+                continue
+            res = fit(jac, klist, jacobian)
+            rows.append((klist, jac, np.asarray(res, dtype=np.float64)))
+    K_max = max(len(r[0]) for r in rows)
+    kl = np.zeros((len(rows), K_max), dtype=np.int32)
+    jc = np.zeros((len(rows), K_max), dtype=np.float64)
+    nk = np.zeros(len(rows), dtype=np.int32)
+    ex = np.zeros((len(rows), 2), dtype=np.float64)
+    for r, (klist, jac, res) in enumerate(rows):
+        nk[r] = len(klist)
+        kl[r, :nk[r]] = klist
+        jc[r, :nk[r]] = jac
+        ex[r] = res
+    np.savez_compressed(os.path.join(HERE, "fit_kmer_curve.npz"), klist=kl, jaccard=jc, n_k=nk, expected=ex)
+    print("fit_kmer_curve:", len(rows), "rows; clamped core:", int((ex[:, 0] == 0).sum()),
+          "clamped acc:", int((ex[:, 1] == 0).sum()))
+
+
+if __name__ == "__main__":
+    json_sketch()
+    refine_grid()
+    fit_kmer_curve()
