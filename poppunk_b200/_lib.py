@@ -1,0 +1,81 @@
+"""ctypes binding of libppb.so — the C ABI declared in include/ppb.h.  No CPU fallback: if the CUDA
+library is missing or fails to load, importing the engine raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libppb.so")
+
+OUT_DISTS, OUT_JACCARD, OUT_COUNTS = 0, 1, 2
+BBITS = 14
+MAX_K = 32
+
+# every symbol include/ppb.h declares (tests check the .so exports each of them)
+SYMBOLS = [
+    "ppb_version", "ppb_last_error", "ppb_device_count", "ppb_square_to_condensed", "ppb_calc_row_idx",
+    "ppb_calc_col_idx", "ppb_num_rows", "ppb_packed_bytes", "ppb_pack_dev", "ppb_query_dev",
+    "ppb_assign_threshold_dev", "ppb_query_host", "ppb_assign_threshold_host", "ppb_microbench_dev",
+    "ppb_launch_count",
+]
+
+
+class Boundary(C.Structure):
+    """``ppb_boundary`` (include/ppb.h)."""
+    _fields_ = [("slope", C.c_int32), ("x_max", C.c_float), ("y_max", C.c_float),
+                ("scale_x", C.c_float), ("scale_y", C.c_float)]
+
+
+class PpbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m poppunk_b200.build` (nvcc, sm_100a). "
+            "This engine has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    i64, i32, vp, f32 = C.c_int64, C.c_int32, C.c_void_p, C.c_float
+    L.ppb_version.restype = C.c_int
+    L.ppb_last_error.restype = C.c_char_p
+    L.ppb_device_count.restype = C.c_int
+    L.ppb_launch_count.restype = i64
+    L.ppb_square_to_condensed.argtypes = [i64, i64, i64]
+    L.ppb_square_to_condensed.restype = i64
+    L.ppb_calc_row_idx.argtypes = [i64, i64]
+    L.ppb_calc_row_idx.restype = i64
+    L.ppb_calc_col_idx.argtypes = [i64, i64, i64]
+    L.ppb_calc_col_idx.restype = i64
+    L.ppb_num_rows.argtypes = [i64, i64, C.c_int]
+    L.ppb_num_rows.restype = i64
+    L.ppb_packed_bytes.argtypes = [i64, i32, i32]
+    L.ppb_packed_bytes.restype = C.c_size_t
+    L.ppb_pack_dev.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp]
+    L.ppb_pack_dev.restype = C.c_int
+    L.ppb_query_dev.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
+    L.ppb_query_dev.restype = C.c_int
+    L.ppb_assign_threshold_dev.argtypes = [vp, i64, i32, f32, f32, vp, vp]
+    L.ppb_assign_threshold_dev.restype = C.c_int
+    L.ppb_query_host.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp,
+                                 vp, i32]
+    L.ppb_query_host.restype = C.c_int
+    L.ppb_assign_threshold_host.argtypes = [vp, i64, i32, f32, f32, vp, i32]
+    L.ppb_assign_threshold_host.restype = C.c_int
+    L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]
+    L.ppb_microbench_dev.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "libppb"):
+    if rc != 0:
+        msg = load().ppb_last_error()
+        raise PpbError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

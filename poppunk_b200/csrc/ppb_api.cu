@@ -1,0 +1,467 @@
+// C ABI of libppb.so (declared in include/ppb.h).  Host-side orchestration only: argument checks,
+// tile scheduling, launches, and the host-buffer convenience path with overlapped copies.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ppb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define PPB_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(PPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+inline int32_t n_slices_of(int32_t ss64) { return (2 * ss64 + 31) / 32; }
+
+// ---- index maps: src/boundary.cpp:18-37 ----------------------------------------------------
+inline int64_t sq2cond(int64_t i, int64_t j, int64_t n) { return n * i - ((i * (i + 1)) >> 1) + j - 1 - i; }
+inline int64_t row_idx(int64_t k, int64_t n) {
+    // boundary.cpp:22-27 plus an exact integer fix-up (the double sqrt alone drifts for huge n)
+    double d = std::sqrt((double)(-8 * k + 4 * n * (n - 1) - 7));
+    int64_t i = n - 2 - (int64_t)std::floor(d / 2.0 - 0.5);
+    i = std::max<int64_t>(0, std::min<int64_t>(i, n - 2));
+    while (i > 0 && sq2cond(i, i + 1, n) > k) i--;
+    while (i < n - 2 && sq2cond(i + 1, i + 2, n) <= k) i++;
+    return i;
+}
+inline int64_t col_idx(int64_t k, int64_t i, int64_t n) {
+    return k + i + 1 - n * (n - 1) / 2 + (n - i) * ((n - i) - 1) / 2;
+}
+
+// ---- tile schedule -----------------------------------------------------------------------
+// Tiles are (64 rows) x (tj columns).  Order: bands of kBand row-tiles; inside a band the column tile is
+// the slow index, so the CTAs running at any moment share a handful of column tiles (L2 hits) and the
+// band's row genomes stay L2-resident while the columns stream past once per band.
+constexpr int kBand = 32;
+
+struct TileKey {
+    int dev;
+    int64_t nA, nB;
+    int self, tj;
+    int64_t i_lo, i_hi;
+    bool operator<(const TileKey &o) const {
+        return std::tie(dev, nA, nB, self, tj, i_lo, i_hi) < std::tie(o.dev, o.nA, o.nB, o.self, o.tj, o.i_lo, o.i_hi);
+    }
+};
+struct TileList {
+    int2 *d = nullptr;
+    int64_t n = 0;
+};
+std::mutex g_tile_mu;
+std::map<TileKey, TileList> g_tiles;
+
+int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
+    std::lock_guard<std::mutex> lk(g_tile_mu);
+    auto it = g_tiles.find(key);
+    if (it != g_tiles.end()) {
+        *out = it->second;
+        return PPB_OK;
+    }
+    std::vector<int2> v;
+    const int64_t nTi = (key.nA + ppb::kTI - 1) / ppb::kTI, nTj = (key.nB + key.tj - 1) / key.tj;
+    const int64_t it_lo = key.i_lo / ppb::kTI, it_hi = key.i_hi / ppb::kTI;
+    for (int64_t b0 = it_lo / kBand * kBand; b0 <= it_hi && b0 < nTi; b0 += kBand) {
+        const int64_t b1 = std::min<int64_t>({b0 + kBand, nTi, it_hi + 1});
+        for (int64_t jt = 0; jt < nTj; jt++)
+            for (int64_t ti = std::max(b0, it_lo); ti < b1; ti++) {
+                if (key.self && jt * key.tj + key.tj - 1 <= ti * ppb::kTI) continue;  // no j > i in this tile
+                v.push_back(make_int2((int)ti, (int)jt));
+            }
+    }
+    TileList tl;
+    tl.n = (int64_t)v.size();
+    if (tl.n) {
+        PPB_CUDA(cudaMalloc(&tl.d, v.size() * sizeof(int2)));
+        PPB_CUDA(cudaMemcpyAsync(tl.d, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+        PPB_CUDA(cudaStreamSynchronize(stream));  // v dies at scope exit
+    }
+    if (g_tiles.size() >= 16) {  // tiny LRU-less cache: drop everything when it grows
+        for (auto &kv : g_tiles) cudaFree(kv.second.d);
+        g_tiles.clear();
+    }
+    g_tiles[key] = tl;
+    *out = tl;
+    return PPB_OK;
+}
+
+int num_sms(int dev, int *out) {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it == cache.end()) {
+        int n = 0;
+        PPB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        it = cache.emplace(dev, n).first;
+    }
+    *out = it->second;
+    return PPB_OK;
+}
+
+int out_row_bytes(int mode, int K) { return mode == PPB_OUT_DISTS ? 8 : 4 * K; }
+
+}  // namespace
+
+extern "C" {
+
+int ppb_version(void) { return PPB_VERSION; }
+const char *ppb_last_error(void) { return g_err.c_str(); }
+int64_t ppb_launch_count(void) { return g_launches.load(); }
+
+int ppb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}
+
+int64_t ppb_square_to_condensed(int64_t i, int64_t j, int64_t n) { return sq2cond(i, j, n); }
+int64_t ppb_calc_row_idx(int64_t k, int64_t n) { return row_idx(k, n); }
+int64_t ppb_calc_col_idx(int64_t k, int64_t i, int64_t n) { return col_idx(k, i, n); }
+int64_t ppb_num_rows(int64_t n_ref, int64_t n_qry, int self) {
+    return self ? n_ref * (n_ref - 1) / 2 : n_ref * n_qry;
+}
+
+size_t ppb_packed_bytes(int64_t n, int32_t K, int32_t sketchsize64) {
+    return (size_t)K * n_slices_of(sketchsize64) * round_up(std::max<int64_t>(n, 1), ppb::kPad) * ppb::kSliceBytes;
+}
+
+int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, int64_t n, int32_t K,
+                 int32_t sketchsize64, uint32_t *d_packed, void *stream) {
+    if (!d_sketch || !d_packed || n < 0 || K < 1 || K > PPB_MAX_K || sketchsize64 < 1)
+        return fail(PPB_ERR_ARG, "ppb_pack_dev: bad argument");
+    if (!d_idx && n != n_src) return fail(PPB_ERR_ARG, "ppb_pack_dev: n != n_src without an index list");
+    const int64_t n_pad = round_up(std::max<int64_t>(n, 1), ppb::kPad);
+    const int64_t total = (int64_t)K * n_slices_of(sketchsize64) * n_pad * ppb::kSliceWords;
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, 148 * 64);
+    ppb::pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        d_sketch, d_idx, n, n_pad, K, sketchsize64, n_slices_of(sketchsize64), d_packed);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
+                  const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
+                  int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                  int64_t row_begin, int64_t row_end, int32_t out_mode, void *d_out,
+                  const ppb_boundary *boundary, int8_t *d_labels, unsigned long long *d_n_degenerate,
+                  void *stream) {
+    const int self = d_qry_packed == nullptr;
+    if (!d_ref_packed || !kmers || K < 1 || K > PPB_MAX_K || n_ref < 0 || (!self && n_qry < 0))
+        return fail(PPB_ERR_ARG, "ppb_query_dev: bad argument");
+    if (sketchsize64 < 1 || sketchsize64 > 1023)
+        return fail(PPB_ERR_ARG, "ppb_query_dev: sketchsize64 must be in [1, 1023] (uint16 per-k counts)");
+    if (out_mode < PPB_OUT_DISTS || out_mode > PPB_OUT_COUNTS) return fail(PPB_ERR_ARG, "ppb_query_dev: bad out_mode");
+    if (!d_out && !(out_mode == PPB_OUT_DISTS && boundary && d_labels))
+        return fail(PPB_ERR_ARG, "ppb_query_dev: no output buffer");
+    if ((boundary != nullptr) != (d_labels != nullptr))
+        return fail(PPB_ERR_ARG, "ppb_query_dev: boundary and d_labels go together");
+    if (boundary && out_mode != PPB_OUT_DISTS) return fail(PPB_ERR_ARG, "ppb_query_dev: labels need PPB_OUT_DISTS");
+    if (boundary && (boundary->slope < 0 || boundary->slope > 2)) return fail(PPB_ERR_ARG, "ppb_query_dev: bad slope");
+    if (d_rand_table && (n_clusters < 1 || !d_ref_cluster || (!self && !d_qry_cluster)))
+        return fail(PPB_ERR_ARG, "ppb_query_dev: random table without cluster ids");
+    for (int t = 1; t < K; t++)
+        if (kmers[t] <= kmers[t - 1]) return fail(PPB_ERR_ARG, "ppb_query_dev: kmers must be ascending");
+    const int64_t total_rows = ppb_num_rows(n_ref, n_qry, self);
+    if (row_begin < 0 || row_end > total_rows || row_begin > row_end)
+        return fail(PPB_ERR_ARG, "ppb_query_dev: bad row range");
+    if (row_begin == row_end) return PPB_OK;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    PPB_CUDA(cudaGetDevice(&dev));
+
+    ppb::QueryParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.self = self;
+    p.A = self ? d_ref_packed : d_qry_packed;
+    p.B = d_ref_packed;
+    p.nA = self ? n_ref : n_qry;
+    p.nB = n_ref;
+    p.nA_pad = round_up(std::max<int64_t>(p.nA, 1), ppb::kPad);
+    p.nB_pad = round_up(std::max<int64_t>(p.nB, 1), ppb::kPad);
+    p.K = K;
+    p.n_slices = n_slices_of(sketchsize64);
+    p.KS = K * p.n_slices;
+    p.G32 = 2 * sketchsize64;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    p.out_mode = out_mode;
+    p.out = d_out;
+    p.labels = d_labels;
+    p.has_boundary = boundary != nullptr;
+    if (boundary) p.bnd = *boundary;
+    p.rand_table = d_rand_table;
+    p.C = n_clusters;
+    p.clB = d_ref_cluster;
+    p.clA = self ? d_ref_cluster : d_qry_cluster;
+    p.n_degenerate = d_n_degenerate;
+    p.S = 64.0 * sketchsize64;
+    p.inv_S = 1.0 / p.S;
+    p.S_pow2 = (sketchsize64 & (sketchsize64 - 1)) == 0;
+    p.tol = (double)PPB_MIN_JACCARD_BINS / p.S;
+    // OLS constants for every possible series length n (the series is always a prefix of kmers)
+    double sx = 0;
+    for (int t = 0; t < K; t++) {
+        p.x[t] = (double)kmers[t];
+        sx += p.x[t];
+        const int n = t + 1;
+        p.xbar[n] = sx / n;
+        double sxx = 0;
+        for (int u = 0; u < n; u++) sxx += (p.x[u] - p.xbar[n]) * (p.x[u] - p.xbar[n]);
+        p.inv_sxx[n] = n >= 2 ? 1.0 / sxx : 0.0;
+        p.inv_n[n] = 1.0 / n;
+    }
+
+    // column-tile width: the widest whose uint16 count buffer fits beside the TMA ring
+    int max_smem = 0;
+    PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int tj = ppb::kMaxTJ;
+    auto smem_need = [&](int tjv) {
+        return (size_t)ppb::kStages * ppb::kStageBytes + (((size_t)K * tjv * ppb::kCntRowWords * 4 + 15) & ~(size_t)15) +
+               2 * ppb::kStages * sizeof(uint64_t);
+    };
+    while (tj > ppb::kJB && smem_need(tj) > (size_t)max_smem) tj >>= 1;
+    if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
+    p.tj = tj;
+
+    TileKey key{dev, p.nA, p.nB, self, tj, 0, 0};
+    if (self) {
+        key.i_lo = row_idx(row_begin, n_ref);
+        key.i_hi = row_idx(row_end - 1, n_ref);
+    } else {
+        key.i_lo = row_begin / n_ref;
+        key.i_hi = (row_end - 1) / n_ref;
+    }
+    TileList tl;
+    if (int rc = get_tiles(key, st, &tl)) return rc;
+    if (tl.n == 0) return PPB_OK;
+    p.tiles = tl.d;
+    p.n_tiles = tl.n;
+
+    int sms = 0;
+    if (int rc = num_sms(dev, &sms)) return rc;
+    const size_t smem = smem_need(tj);
+    static std::mutex attr_mu;
+    {
+        std::lock_guard<std::mutex> lk(attr_mu);
+        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(tl.n, sms);
+    ppb::query_kernel<<<grid, ppb::kThreads, smem, st>>>(p);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, float x_max, float y_max,
+                             float *d_out, void *stream) {
+    if (n < 0 || (n > 0 && (!d_dists || !d_out)) || slope < 0 || slope > 2)
+        return fail(PPB_ERR_ARG, "ppb_assign_threshold_dev: bad argument");
+    if (n == 0) return PPB_OK;
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>((n + threads - 1) / threads, 148 * 32);
+    ppb::threshold_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(d_dists), n, slope, x_max, y_max, d_out);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *lane_ops, void *stream) {
+    if (mode < 0 || mode > 3 || iters < 1 || !d_sink) return fail(PPB_ERR_ARG, "ppb_microbench_dev: bad argument");
+    int dev = 0, sms = 0;
+    PPB_CUDA(cudaGetDevice(&dev));
+    if (int rc = num_sms(dev, &sms)) return rc;
+    const unsigned grid = sms * 2, threads = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t per_thread_iter = 0;
+    switch (mode) {
+        case 0: ppb::microbench_kernel<0><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
+        case 1: ppb::microbench_kernel<1><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
+        case 2: ppb::microbench_kernel<2><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
+        default: ppb::microbench_kernel<3><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 8; break;
+    }
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    // lane-ops of the op being measured (mode 2 counts its LOP3s)
+    if (lane_ops) *lane_ops = (int64_t)grid * threads * iters * per_thread_iter;
+    return PPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path: H2D, pack, row-chunked kernel launches, D2H overlapped on a second stream.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(PPB_ERR_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+        }
+        return PPB_OK;
+    }
+};
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() {
+        if (s) cudaStreamDestroy(s);
+    }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    ~Event() {
+        if (e) cudaEventDestroy(e);
+    }
+};
+}  // namespace
+
+int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int64_t n_qry, const int32_t *kmers,
+                   int32_t K, int32_t sketchsize64, int32_t bbits, const float *rand_table, int32_t n_clusters,
+                   const uint16_t *ref_cluster, const uint16_t *qry_cluster, int64_t row_begin, int64_t row_end,
+                   int32_t out_mode, void *out, const ppb_boundary *boundary, int8_t *labels,
+                   int64_t *n_degenerate, int32_t device_id) {
+    if (bbits != PPB_BBITS) return fail(PPB_ERR_ARG, "ppb_query_host: bbits must be 14");
+    if (!ref || !kmers || K < 1 || K > PPB_MAX_K || sketchsize64 < 1 || n_ref < 0)
+        return fail(PPB_ERR_ARG, "ppb_query_host: bad argument");
+    const int self = qry == nullptr;
+    const int64_t total_rows = ppb_num_rows(n_ref, n_qry, self);
+    if (row_begin < 0 || row_end > total_rows || row_begin > row_end)
+        return fail(PPB_ERR_ARG, "ppb_query_host: bad row range");
+    if (n_degenerate) *n_degenerate = 0;
+    if (row_begin == row_end) return PPB_OK;
+    int ndev = ppb_device_count();
+    if (ndev <= 0) return fail(PPB_ERR_NO_DEVICE, "ppb_query_host: no CUDA device (this engine has no CPU path)");
+    if (device_id < 0 || device_id >= ndev) return fail(PPB_ERR_ARG, "ppb_query_host: bad device id");
+    PPB_CUDA(cudaSetDevice(device_id));
+
+    Stream s_compute, s_copy;
+    PPB_CUDA(cudaStreamCreateWithFlags(&s_compute.s, cudaStreamNonBlocking));
+    PPB_CUDA(cudaStreamCreateWithFlags(&s_copy.s, cudaStreamNonBlocking));
+
+    const int64_t W = (int64_t)sketchsize64 * PPB_BBITS;
+    const size_t ref_bytes = (size_t)n_ref * K * W * 8, qry_bytes = self ? 0 : (size_t)n_qry * K * W * 8;
+    DevBuf d_ref_raw, d_qry_raw, d_ref, d_qry, d_tab, d_rc, d_qc, d_deg;
+    if (int rc = d_ref_raw.alloc(ref_bytes)) return rc;
+    if (int rc = d_ref.alloc(ppb_packed_bytes(n_ref, K, sketchsize64))) return rc;
+    PPB_CUDA(cudaMemcpyAsync(d_ref_raw.p, ref, ref_bytes, cudaMemcpyHostToDevice, s_compute.s));
+    if (int rc = ppb_pack_dev((const uint64_t *)d_ref_raw.p, n_ref, nullptr, n_ref, K, sketchsize64, (uint32_t *)d_ref.p,
+                              s_compute.s))
+        return rc;
+    if (!self) {
+        if (int rc = d_qry_raw.alloc(qry_bytes)) return rc;
+        if (int rc = d_qry.alloc(ppb_packed_bytes(n_qry, K, sketchsize64))) return rc;
+        PPB_CUDA(cudaMemcpyAsync(d_qry_raw.p, qry, qry_bytes, cudaMemcpyHostToDevice, s_compute.s));
+        if (int rc = ppb_pack_dev((const uint64_t *)d_qry_raw.p, n_qry, nullptr, n_qry, K, sketchsize64,
+                                  (uint32_t *)d_qry.p, s_compute.s))
+            return rc;
+    }
+    if (rand_table) {
+        if (n_clusters < 1 || !ref_cluster || (!self && !qry_cluster))
+            return fail(PPB_ERR_ARG, "ppb_query_host: random table without cluster ids");
+        const size_t tb = (size_t)n_clusters * n_clusters * K * sizeof(float);
+        if (int rc = d_tab.alloc(tb)) return rc;
+        if (int rc = d_rc.alloc((size_t)n_ref * 2)) return rc;
+        PPB_CUDA(cudaMemcpyAsync(d_tab.p, rand_table, tb, cudaMemcpyHostToDevice, s_compute.s));
+        PPB_CUDA(cudaMemcpyAsync(d_rc.p, ref_cluster, (size_t)n_ref * 2, cudaMemcpyHostToDevice, s_compute.s));
+        if (!self) {
+            if (int rc = d_qc.alloc((size_t)n_qry * 2)) return rc;
+            PPB_CUDA(cudaMemcpyAsync(d_qc.p, qry_cluster, (size_t)n_qry * 2, cudaMemcpyHostToDevice, s_compute.s));
+        }
+    }
+    if (int rc = d_deg.alloc(8)) return rc;
+    PPB_CUDA(cudaMemsetAsync(d_deg.p, 0, 8, s_compute.s));
+
+    // row chunks, double-buffered: kernel(c) on s_compute overlaps D2H(c-1) on s_copy
+    const int rb = out_row_bytes(out_mode, K);
+    const int64_t rows = row_end - row_begin;
+    size_t free_b = 0, total_b = 0;
+    PPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t chunk = std::min<int64_t>(rows, (int64_t)1 << 27);  // 128 Mi rows = 1 GiB of float2 per buffer
+    const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
+    while (chunk > 1024 && (size_t)(2 * chunk * per_row) > free_b / 2) chunk >>= 1;
+    DevBuf d_out[2], d_lab[2];
+    Event done_compute[2], done_copy[2];
+    for (int b = 0; b < 2; b++) {
+        if (out)
+            if (int rc = d_out[b].alloc((size_t)chunk * rb)) return rc;
+        if (labels)
+            if (int rc = d_lab[b].alloc((size_t)chunk)) return rc;
+        PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
+        PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
+    }
+    int64_t c = 0;
+    for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk, c++) {
+        const int b = (int)(c & 1);
+        const int64_t r1 = std::min(row_end, r0 + chunk);
+        if (c >= 2) PPB_CUDA(cudaStreamWaitEvent(s_compute.s, done_copy[b].e, 0));  // buffer b drained
+        if (int rc = ppb_query_dev((const uint32_t *)d_ref.p, n_ref, self ? nullptr : (const uint32_t *)d_qry.p, n_qry,
+                                   kmers, K, sketchsize64, (const float *)d_tab.p, n_clusters,
+                                   (const uint16_t *)d_rc.p, (const uint16_t *)d_qc.p, r0, r1, out_mode,
+                                   out ? d_out[b].p : nullptr, boundary, labels ? (int8_t *)d_lab[b].p : nullptr,
+                                   (unsigned long long *)d_deg.p, s_compute.s))
+            return rc;
+        PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
+        PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
+        if (out)
+            PPB_CUDA(cudaMemcpyAsync((char *)out + (size_t)(r0 - row_begin) * rb, d_out[b].p, (size_t)(r1 - r0) * rb,
+                                     cudaMemcpyDeviceToHost, s_copy.s));
+        if (labels)
+            PPB_CUDA(cudaMemcpyAsync(labels + (r0 - row_begin), d_lab[b].p, (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
+                                     s_copy.s));
+        PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
+    }
+    unsigned long long deg = 0;
+    PPB_CUDA(cudaMemcpyAsync(&deg, d_deg.p, 8, cudaMemcpyDeviceToHost, s_compute.s));
+    PPB_CUDA(cudaStreamSynchronize(s_compute.s));
+    PPB_CUDA(cudaStreamSynchronize(s_copy.s));
+    if (n_degenerate) *n_degenerate = (int64_t)deg;
+    return PPB_OK;
+}
+
+int ppb_assign_threshold_host(const float *dists, int64_t n, int32_t slope, float x_max, float y_max, float *out,
+                              int32_t device_id) {
+    if (n < 0 || (n > 0 && (!dists || !out))) return fail(PPB_ERR_ARG, "ppb_assign_threshold_host: bad argument");
+    if (n == 0) return PPB_OK;
+    int ndev = ppb_device_count();
+    if (ndev <= 0) return fail(PPB_ERR_NO_DEVICE, "ppb_assign_threshold_host: no CUDA device (no CPU path)");
+    if (device_id < 0 || device_id >= ndev) return fail(PPB_ERR_ARG, "ppb_assign_threshold_host: bad device id");
+    PPB_CUDA(cudaSetDevice(device_id));
+    DevBuf d_in, d_o;
+    if (int rc = d_in.alloc((size_t)n * 8)) return rc;
+    if (int rc = d_o.alloc((size_t)n * 4)) return rc;
+    PPB_CUDA(cudaMemcpy(d_in.p, dists, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (int rc = ppb_assign_threshold_dev((const float *)d_in.p, n, slope, x_max, y_max, (float *)d_o.p, nullptr)) return rc;
+    PPB_CUDA(cudaMemcpy(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return PPB_OK;
+}
+
+}  // extern "C"

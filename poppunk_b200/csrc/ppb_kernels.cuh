@@ -1,0 +1,395 @@
+// Device kernels of the B200 sketch-distance engine (sm_100a only).
+//
+//   pack_kernel      canonical uint64 [n][K][W] bindash sketches  ->  lane-sliced layout (below)
+//   query_kernel     the hot path: per-k matching-bin counts (XOR/AND-NOT + POPC, a4), random-match
+//                    correction (a5), log-linear fit (a6), optional assign_threshold epilogue (a7);
+//                    one coalesced float2 store per pair in PopPUNK's row order (a2/a8)
+//   threshold_kernel standalone assign_threshold (src/boundary.cpp:60-80)
+//
+// PACKED ("lane-sliced") LAYOUT.  A sketch for one k is viewed as G32 = 2*sketchsize64 groups of 32 bins
+// (group g = 2*s + h is the low (h=0) / high (h=1) half of the 64-bit column s); a group has 14 plane
+// words.  Groups are cut into slices of 32: lane l of slice t owns group 32*t + l.  One (genome, k, slice)
+// is 448 uint32 = 1792 B:
+//     words [q*128 + l*4 + e], q=0..2, e=0..3 : plane 4q+e of lane l      (three conflict-free LDS.128)
+//     words [384 + l*2 + e],   e=0..1         : plane 12+e  of lane l      (one LDS.64)
+// and the whole array is  uint32 [K*n_slices][n_pad][448]  (k-slice-major, genome-minor), so the JB
+// consecutive genomes a pipeline stage needs are ONE contiguous 28 KB TMA bulk copy.
+//
+// MAPPING (why it looks like this — DESIGN.md has the numbers).  The work per pair is 14 LOP3 per group of
+// 32 bins and nothing else of weight, so the kernel is bound by the INT32 logic pipe, not by HBM.  Each
+// warp keeps 8 "row" genomes (i) of the current (k, slice) stationary in registers (8 x 14 words per lane:
+// the register file is the A-tile), streams "column" genomes (j) through shared memory (TMA-fed ring, one
+// LDS.128 feeds 4 x 8 LOP3), and gets the per-pair count with a POPC per lane and one warp REDUX per two
+// pairs.  Per-k counts wait in shared memory (uint16) until every k is done, then the same CTA runs the
+// regression in float64 and writes the row-ordered outputs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ppb.h"
+#include "ppb_ptx.cuh"
+
+namespace ppb {
+
+constexpr int kBbits = 14;
+constexpr int kSliceWords = 448;              // 32 lanes x 14 planes
+constexpr int kSliceBytes = kSliceWords * 4;  // 1792
+constexpr int kRowsPerWarp = 8;               // register-stationary genomes per warp
+constexpr int kComputeWarps = 8;
+constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
+constexpr int kJB = 16;                            // column genomes per pipeline stage
+constexpr int kStages = 3;
+constexpr int kStageBytes = kJB * kSliceBytes;     // 28672
+constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
+constexpr int kThreads = (kComputeWarps + 1) * 32; // + 1 TMA producer warp
+constexpr int kPad = 128;                          // genome padding of packed arrays
+constexpr int kMaxTJ = 128;
+
+struct QueryParams {
+    const uint32_t *A;  // packed rows   (queries; == B in self mode)
+    const uint32_t *B;  // packed columns (refs)
+    int64_t nA, nB, nA_pad, nB_pad;
+    int32_t K, n_slices, KS, G32;
+    int32_t self, tj;
+    const int2 *tiles;
+    int64_t n_tiles;
+    int64_t row_begin, row_end;
+    int32_t out_mode;
+    void *out;
+    int8_t *labels;
+    int32_t has_boundary;
+    ppb_boundary bnd;
+    const float *rand_table;
+    int32_t C;
+    const uint16_t *clA, *clB;
+    unsigned long long *n_degenerate;
+    double S, inv_S, tol;
+    int32_t S_pow2;
+    double x[PPB_MAX_K];
+    double xbar[PPB_MAX_K + 1], inv_sxx[PPB_MAX_K + 1], inv_n[PPB_MAX_K + 1];
+};
+
+// ------------------------------------------------------------------------------------------------
+// pack: one thread per output word.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const uint64_t *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
+                            int64_t n_pad, int32_t K, int32_t ss64, int32_t n_slices,
+                            uint32_t *__restrict__ dst) {
+    const int64_t total = (int64_t)K * n_slices * n_pad * kSliceWords;
+    const int64_t W = (int64_t)ss64 * kBbits;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t w = (int32_t)(o % kSliceWords);
+        const int64_t gk = o / kSliceWords;
+        const int64_t g = gk % n_pad;
+        const int32_t ks = (int32_t)(gk / n_pad);
+        const int32_t k = ks / n_slices, sl = ks - k * n_slices;
+        int32_t lane, plane;
+        if (w < 384) {
+            lane = (w & 127) >> 2;
+            plane = ((w >> 7) << 2) + (w & 3);
+        } else {
+            lane = (w - 384) >> 1;
+            plane = 12 + (w & 1);
+        }
+        const int32_t grp = sl * 32 + lane;
+        uint32_t v = 0;
+        if (g < n && grp < 2 * ss64) {
+            const int64_t row = idx ? idx[g] : g;
+            const uint64_t word = src[(row * K + k) * W + (int64_t)(grp >> 1) * kBbits + plane];
+            v = (grp & 1) ? (uint32_t)(word >> 32) : (uint32_t)word;
+        }
+        dst[o] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a7: src/boundary.cpp:42-58 line_dist — float32, the reference's operation order, no FMA contraction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float line_dist(float x0, float y0, float x_max, float y_max, int slope) {
+    float side = 0.0f;
+    if (slope == 2) {
+        if (x_max == 0.0f || y_max == 0.0f) {
+            side = __fsqrt_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)));
+        } else {
+            side = __fsub_rn(__fadd_rn(__fmul_rn(y0, x_max), __fmul_rn(x0, y_max)), __fmul_rn(x_max, y_max));
+        }
+    } else if (slope == 0) {
+        side = __fsub_rn(x0, x_max);
+    } else if (slope == 1) {
+        side = __fsub_rn(y0, y_max);
+    }
+    return side;
+}
+__device__ __forceinline__ float boundary_side(float in_tri) {  // boundary.cpp:68-76
+    return in_tri == 0.0f ? 0.0f : (in_tri > 0.0f ? 1.0f : -1.0f);
+}
+
+__global__ void threshold_kernel(const float2 *__restrict__ d, int64_t n, int32_t slope, float x_max,
+                                 float y_max, float *__restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const float2 v = d[r];
+        out[r] = boundary_side(line_dist(v.x, v.y, x_max, y_max, slope));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-pair epilogue: counts (shared memory) -> Jaccard -> truncated log-linear fit -> outputs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int tj, int jl, int il) {
+    const uint32_t w = cnt[(t * tj + jl) * kCntRowWords + (il >> 1)];
+    return (il & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+__device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32_t *cnt, int jl, int il,
+                                              int64_t i, int64_t j, int64_t row, bool &degenerate) {
+    const int K = p.K;
+    const float *rt = nullptr;
+    if (p.rand_table) rt = p.rand_table + ((int64_t)p.clB[j] * p.C + p.clA[i]) * K;
+
+    if (p.out_mode == PPB_OUT_COUNTS) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(p.out) + row * K;
+        for (int t = 0; t < K; t++) o[t] = read_count(cnt, t, p.tj, jl, il);
+        return;
+    }
+    double sy = 0.0, sxy = 0.0;
+    int n = 0;
+    bool open = true;
+    for (int t = 0; t < K; t++) {
+        const double c = (double)read_count(cnt, t, p.tj, jl, il);
+        double jac = p.S_pow2 ? c * p.inv_S : c / p.S;
+        if (rt) {  // observed_excess(obs, r, 1): max(0, obs - r) / (1 - r)
+            const double r = (double)__ldg(rt + t);
+            double diff = jac - r;
+            if (diff < 0.0) diff = 0.0;
+            jac = diff / (1.0 - r);
+        }
+        if (p.out_mode == PPB_OUT_JACCARD) {
+            reinterpret_cast<float *>(p.out)[row * K + t] = (float)jac;
+            continue;
+        }
+        if (open) {
+            if (jac < p.tol) {
+                open = false;  // this k and every larger one are ignored (docs/sketching.rst:161-165)
+            } else {
+                const double y = log(jac);
+                sy += y;
+                sxy += p.x[t] * y;
+                n++;
+            }
+        }
+    }
+    if (p.out_mode == PPB_OUT_JACCARD) return;
+
+    float core = 0.0f, acc = 0.0f;
+    if (n < 2) {
+        degenerate = true;
+    } else {
+        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
+        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];     // intercept = log(1 - acc)
+        core = beta < 0.0 ? (float)(1.0 - exp(beta)) : 0.0f;
+        acc = alpha < 0.0 ? (float)(1.0 - exp(alpha)) : 0.0f;
+    }
+    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    if (p.has_boundary) {
+        // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
+        const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
+        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The hot path.  Persistent CTAs (one per SM), 8 compute warps + 1 TMA producer warp.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constant__ QueryParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *stage_base = smem;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes);
+    const int cnt_words = p.K * p.tj * kCntRowWords;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + ((cnt_words * 4 + 15) & ~15));
+    uint64_t *empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kComputeWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int tj = p.tj, n_jb = tj / kJB, KS = p.KS;
+
+    if (warp == kComputeWarps) {
+        // ===== TMA producer: streams column-genome slices of every (tile, k, slice) into the ring =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int2 tc = p.tiles[tile];
+                const int64_t j0 = (int64_t)tc.y * tj;
+                for (int ks = 0; ks < KS; ks++) {
+                    const uint32_t *src = p.B + ((int64_t)ks * p.nB_pad + j0) * kSliceWords;
+                    for (int jb = 0; jb < n_jb; jb++, it++) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[s], kStageBytes);
+                        tma_load_1d(stage_base + s * kStageBytes, src + (int64_t)jb * kJB * kSliceWords,
+                                    kStageBytes, &full[s]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int2 tc = p.tiles[tile];
+        const int64_t i0 = (int64_t)tc.x * kTI, j0 = (int64_t)tc.y * tj;
+
+        for (int ks = 0; ks < KS; ks++) {
+            const int k = ks / p.n_slices, sl = ks - k * p.n_slices;
+            const uint32_t valid = (sl * 32 + lane < p.G32) ? 0xffffffffu : 0u;
+            const bool accumulate = sl != 0;  // later slices of the same k add to the stored counts
+
+            // register-stationary row genomes: 8 x 14 plane words of this lane's group
+            uint32_t a[kRowsPerWarp][kBbits];
+            {
+                const uint32_t *ap = p.A + ((int64_t)ks * p.nA_pad + i0 + warp * kRowsPerWarp) * kSliceWords;
+#pragma unroll
+                for (int g = 0; g < kRowsPerWarp; g++) {
+                    const uint4 *q4 = reinterpret_cast<const uint4 *>(ap + g * kSliceWords);
+                    const uint4 v0 = __ldg(q4 + lane), v1 = __ldg(q4 + 32 + lane), v2 = __ldg(q4 + 64 + lane);
+                    const uint2 v3 = __ldg(reinterpret_cast<const uint2 *>(ap + g * kSliceWords + 384) + lane);
+                    a[g][0] = v0.x, a[g][1] = v0.y, a[g][2] = v0.z, a[g][3] = v0.w;
+                    a[g][4] = v1.x, a[g][5] = v1.y, a[g][6] = v1.z, a[g][7] = v1.w;
+                    a[g][8] = v2.x, a[g][9] = v2.y, a[g][10] = v2.z, a[g][11] = v2.w;
+                    a[g][12] = v3.x, a[g][13] = v3.y;
+                }
+            }
+            uint32_t *cnt_k = cnt + k * tj * kCntRowWords + warp * (kRowsPerWarp / 2);
+
+            for (int jb = 0; jb < n_jb; jb++, it++) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                mbar_wait(&full[s], ph);
+                const uint8_t *sb = stage_base + s * kStageBytes;
+#pragma unroll 2
+                for (int jj = 0; jj < kJB; jj++) {
+                    const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
+                    const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
+                    const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];
+                    uint32_t c[kRowsPerWarp];
+#pragma unroll
+                    for (int g = 0; g < kRowsPerWarp; g++) {
+                        uint32_t bits = valid;
+                        bits = and_xnor(bits, a[g][0], b0.x);
+                        bits = and_xnor(bits, a[g][1], b0.y);
+                        bits = and_xnor(bits, a[g][2], b0.z);
+                        bits = and_xnor(bits, a[g][3], b0.w);
+                        bits = and_xnor(bits, a[g][4], b1.x);
+                        bits = and_xnor(bits, a[g][5], b1.y);
+                        bits = and_xnor(bits, a[g][6], b1.z);
+                        bits = and_xnor(bits, a[g][7], b1.w);
+                        bits = and_xnor(bits, a[g][8], b2.x);
+                        bits = and_xnor(bits, a[g][9], b2.y);
+                        bits = and_xnor(bits, a[g][10], b2.z);
+                        bits = and_xnor(bits, a[g][11], b2.w);
+                        bits = and_xnor(bits, a[g][12], b3.x);
+                        bits = and_xnor(bits, a[g][13], b3.y);
+                        c[g] = __popc(bits);
+                    }
+                    // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
+                    const uint32_t r0 = __reduce_add_sync(0xffffffffu, c[0] + (c[1] << 16));
+                    const uint32_t r1 = __reduce_add_sync(0xffffffffu, c[2] + (c[3] << 16));
+                    const uint32_t r2 = __reduce_add_sync(0xffffffffu, c[4] + (c[5] << 16));
+                    const uint32_t r3 = __reduce_add_sync(0xffffffffu, c[6] + (c[7] << 16));
+                    if (lane == 0) {  // one STS.128: this warp's 8 counts of column (jb, jj)
+                        uint4 *dst = reinterpret_cast<uint4 *>(cnt_k + (jb * kJB + jj) * kCntRowWords);
+                        uint4 v = make_uint4(r0, r1, r2, r3);
+                        if (accumulate) {
+                            const uint4 o = *dst;
+                            v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+                        }
+                        *dst = v;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+        }
+        bar_sync(1, kComputeWarps * 32);  // every warp's counts for every k are in shared memory
+
+        // ===== epilogue: consecutive lanes -> consecutive columns j -> coalesced row-order stores =====
+        {
+            const int tid = threadIdx.x;
+            const int tj_shift = 31 - __clz(tj);
+            bool degenerate_any = false;
+            for (int pi = tid; pi < kTI * tj; pi += kComputeWarps * 32) {
+                const int jl = pi & (tj - 1), il = pi >> tj_shift;
+                const int64_t i = i0 + il, j = j0 + jl;
+                bool ok;
+                int64_t row;
+                if (p.self) {
+                    ok = (i < j) && (j < p.nB);
+                    row = p.nB * i - ((i * (i + 1)) >> 1) + j - 1 - i;  // boundary.cpp:33-37
+                } else {
+                    ok = (i < p.nA) && (j < p.nB);
+                    row = i * p.nB + j;  // utils.py:224-226
+                }
+                ok = ok && row >= p.row_begin && row < p.row_end;
+                bool deg = false;
+                if (ok) pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
+                degenerate_any |= deg;
+                if (p.n_degenerate) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, deg);
+                    if (m && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)__popc(m));
+                }
+            }
+            (void)degenerate_any;
+        }
+        bar_sync(1, kComputeWarps * 32);  // counts consumed before the next tile overwrites them
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-pipe micro-roofline kernels (bench.py reports the hot kernel against these).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) microbench_kernel(int64_t iters, uint32_t *sink, uint32_t seed) {
+    uint32_t x[8], av[14], acc = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) x[g] = seed * (threadIdx.x + 1) + g * 0x9e3779b9u;
+#pragma unroll
+    for (int r = 0; r < 14; r++) av[r] = (seed ^ (blockIdx.x * 2654435761u)) + r * 0x85ebca6bu;
+    for (int64_t i = 0; i < iters; i++) {
+        if (MODE == 0) {  // LOP3 only: 8 independent chains x 14 (the hot loop's dependency shape)
+#pragma unroll
+            for (int r = 0; r < 14; r++)
+#pragma unroll
+                for (int g = 0; g < 8; g++) x[g] = and_xnor(x[g], av[r], av[(r + g) % 14]);
+        } else if (MODE == 1) {  // POPC only
+#pragma unroll
+            for (int r = 0; r < 14; r++)
+#pragma unroll
+                for (int g = 0; g < 8; g++) x[g] = __popc(x[g]);
+        } else if (MODE == 2) {  // the hot loop's mix: 14 LOP3 : 1 POPC : 1 IADD
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                uint32_t bits = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < 14; r++) bits = and_xnor(bits, av[r], x[g]);
+                x[g] += __popc(bits);
+            }
+        } else {  // MODE 3: warp REDUX
+#pragma unroll
+            for (int g = 0; g < 8; g++) x[g] = __reduce_add_sync(0xffffffffu, x[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++) acc ^= x[g];
+    if (acc == 0x12345678u) sink[0] = acc;  // keep the work alive
+}
+
+}  // namespace ppb

@@ -1,0 +1,281 @@
+"""Host-side engine: torch tensors hold the sketches / results in HBM, the work is done by the
+hand-written sm_100a kernels in ``libppb.so`` through the C ABI (``include/ppb.h``).
+
+torch is plumbing here (device memory, streams, ``torch.distributed``); there is no torch compute on
+the hot path and no CPU fallback — every entry point raises if the CUDA library or a GPU is missing.
+
+Replaces the native part of ``pp_sketchlib.queryDatabase`` (call sites PopPUNK/sketchlib.py:528-537,
+584-593) once the sketches are in memory; ``poppunk_b200.sketchlib.queryDatabase`` is the drop-in wrapper.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OUT_COUNTS, OUT_DISTS, OUT_JACCARD, BBITS, Boundary, check
+
+__all__ = ["PackedSketches", "pack", "query", "query_host", "assign_threshold", "num_rows", "shard_rows",
+           "query_sharded", "OUT_DISTS", "OUT_JACCARD", "OUT_COUNTS"]
+
+
+def _require_cuda(device=None) -> torch.device:
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("poppunk_b200: no CUDA device visible — this engine has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("poppunk_b200: tensors must live on a CUDA device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _stream_ptr(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def num_rows(n_ref: int, n_qry: Optional[int] = None) -> int:
+    """Rows of the result: condensed upper triangle (self) or query-major rectangle (utils.py:199-226)."""
+    return n_ref * (n_ref - 1) // 2 if n_qry is None else n_ref * n_qry
+
+
+@dataclass
+class PackedSketches:
+    """Sketches of ``n`` genomes in the kernel's lane-sliced HBM layout (csrc/ppb_kernels.cuh)."""
+    data: torch.Tensor            # uint8 [ppb_packed_bytes]
+    n: int
+    K: int
+    sketchsize64: int
+    clusters: Optional[torch.Tensor] = None   # uint16-as-int16 [n] random-match cluster ids
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def as_device_sketches(sketches, device=None) -> torch.Tensor:
+    """uint64 ``[n][K][W]`` (numpy or torch, host or device) -> int64-viewed CUDA tensor (bit-identical)."""
+    dev = _require_cuda(device)
+    if isinstance(sketches, np.ndarray):
+        if sketches.dtype != np.uint64:
+            raise TypeError("sketch arrays are uint64")
+        sketches = torch.from_numpy(np.ascontiguousarray(sketches).view(np.int64))
+    if sketches.dtype == torch.uint64:
+        sketches = sketches.view(torch.int64)
+    if sketches.dtype != torch.int64 or sketches.dim() != 3:
+        raise TypeError("sketches must be uint64 [n][K][W]")
+    return sketches.to(dev, non_blocking=True).contiguous()
+
+
+def pack(sketches, idx=None, clusters=None, device=None) -> PackedSketches:
+    """Gather genomes ``idx`` (list order = output order, the rList/qList semantics of
+    pp_sketchlib.queryDatabase) and re-lay them for the kernel.  One memory-bound pass."""
+    L = _lib.load()
+    sk = as_device_sketches(sketches, device)
+    dev = sk.device
+    n_src, K, W = sk.shape
+    if W % BBITS:
+        raise ValueError("W must be sketchsize64 * 14")
+    ss64 = W // BBITS
+    idx_t = None
+    n = n_src
+    if idx is not None:
+        idx_t = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(dev)
+        n = idx_t.numel()
+        if n and (int(idx_t.min()) < 0 or int(idx_t.max()) >= n_src):
+            raise IndexError("genome index out of range")
+    out = torch.empty(L.ppb_packed_bytes(n, K, ss64), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(L.ppb_pack_dev(sk.data_ptr(), n_src, idx_t.data_ptr() if idx_t is not None else None, n, K, ss64,
+                             out.data_ptr(), _stream_ptr(dev)), "ppb_pack_dev")
+    cl = None
+    if clusters is not None:
+        cl_np = np.ascontiguousarray(clusters, dtype=np.uint16)
+        if idx is not None:
+            cl_np = cl_np[np.asarray(idx, dtype=np.int64)]
+        cl = torch.from_numpy(cl_np.view(np.int16)).to(dev)
+    return PackedSketches(out, n, K, ss64, cl)
+
+
+def _boundary(boundary) -> Optional[Boundary]:
+    if boundary is None:
+        return None
+    if isinstance(boundary, Boundary):
+        return boundary
+    slope, x_max, y_max, *scale = boundary
+    sx, sy = (scale + [1.0, 1.0])[:2] if scale else (1.0, 1.0)
+    return Boundary(int(slope), float(x_max), float(y_max), float(sx), float(sy))
+
+
+def query(ref: PackedSketches, qry: Optional[PackedSketches], kmers: Sequence[int], rand_table=None,
+          row_begin: int = 0, row_end: Optional[int] = None, out_mode: int = OUT_DISTS, boundary=None,
+          want_out: bool = True, out: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+          n_degenerate: Optional[torch.Tensor] = None):
+    """Launch the distance kernel on the current stream; everything stays on the device.
+
+    Returns ``(out, labels, n_degenerate)``: ``out`` float32 ``[rows][2]`` (DISTS), float32 ``[rows][K]``
+    (JACCARD) or int32 ``[rows][K]`` (COUNTS; uint32 bit pattern); ``labels`` int8 ``[rows]`` when a
+    ``boundary=(slope, x_max, y_max[, scale_x, scale_y])`` is given; ``n_degenerate`` int64 ``[1]`` device
+    counter of rows whose fit had fewer than two usable k (they are (0, 0)).
+    """
+    L = _lib.load()
+    dev = _require_cuda(ref.device)
+    self_mode = qry is None
+    if not self_mode and (qry.K != ref.K or qry.sketchsize64 != ref.sketchsize64 or qry.device != ref.device):
+        raise ValueError("query and reference sketches differ in k-mers, sketch size or device")
+    kmers_np = np.ascontiguousarray(kmers, dtype=np.int32)
+    K = ref.K
+    if kmers_np.shape != (K,):
+        raise ValueError("klist length does not match the packed sketches")
+    total = num_rows(ref.n, None if self_mode else qry.n)
+    if row_end is None:
+        row_end = total
+    rows = row_end - row_begin
+    if rows < 0:
+        raise ValueError("bad row range")
+    bnd = _boundary(boundary)
+    tab = None
+    C_ = 0
+    if rand_table is not None:
+        tab = torch.as_tensor(np.ascontiguousarray(rand_table, dtype=np.float32) if isinstance(rand_table, np.ndarray)
+                              else rand_table, dtype=torch.float32).to(dev).contiguous()
+        C_ = tab.shape[0]
+        if tuple(tab.shape) != (C_, C_, K):
+            raise ValueError("random-match table must be [C][C][K]")
+        if ref.clusters is None or (not self_mode and qry.clusters is None):
+            raise ValueError("random-match table given but sketches carry no cluster ids")
+    if want_out and out is None:
+        if out_mode == OUT_DISTS:
+            out = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+        elif out_mode == OUT_JACCARD:
+            out = torch.empty((rows, K), dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty((rows, K), dtype=torch.int32, device=dev)
+    if bnd is not None and labels is None:
+        labels = torch.empty(rows, dtype=torch.int8, device=dev)
+    if n_degenerate is None:
+        n_degenerate = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(L.ppb_query_dev(
+            ref.data.data_ptr(), ref.n, None if self_mode else qry.data.data_ptr(), 0 if self_mode else qry.n,
+            kmers_np.ctypes.data, K, ref.sketchsize64,
+            tab.data_ptr() if tab is not None else None, C_,
+            ref.clusters.data_ptr() if (tab is not None) else None,
+            qry.clusters.data_ptr() if (tab is not None and not self_mode) else None,
+            row_begin, row_end, out_mode, out.data_ptr() if out is not None else None,
+            C.byref(bnd) if bnd is not None else None, labels.data_ptr() if bnd is not None else None,
+            n_degenerate.data_ptr(), _stream_ptr(dev)), "ppb_query_dev")
+    return out, (labels if bnd is not None else None), n_degenerate
+
+
+def assign_threshold(dists: torch.Tensor, slope: int, x_max: float, y_max: float) -> torch.Tensor:
+    """Device twin of ``poppunk_refine.assignThreshold`` (src/boundary.cpp:60-80): float32 [n] in {-1,0,1}."""
+    L = _lib.load()
+    dev = _require_cuda(dists.device)
+    if dists.dtype != torch.float32 or dists.dim() != 2 or dists.shape[1] != 2 or not dists.is_contiguous():
+        raise TypeError("distMat must be float32, C-contiguous, shape (n, 2)")  # python_bindings.cpp:82 .noconvert()
+    out = torch.empty(dists.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(L.ppb_assign_threshold_dev(dists.data_ptr(), dists.shape[0], int(slope), float(x_max), float(y_max),
+                                         out.data_ptr(), _stream_ptr(dev)), "ppb_assign_threshold_dev")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# host-buffer path (H2D + pack + kernels + D2H inside the library) — what the drop-in wrapper uses
+# --------------------------------------------------------------------------------------------
+def query_host(ref: np.ndarray, qry: Optional[np.ndarray], kmers, rand_table=None, ref_cluster=None,
+               qry_cluster=None, row_begin: int = 0, row_end: Optional[int] = None, out_mode: int = OUT_DISTS,
+               boundary=None, out: Optional[np.ndarray] = None, want_out: bool = True, device_id: int = 0):
+    """``ppb_query_host``: NumPy in, NumPy out.  Returns ``(out, labels, n_degenerate)``."""
+    L = _lib.load()
+    if L.ppb_device_count() <= 0:
+        raise RuntimeError("poppunk_b200: no CUDA device visible — this engine has no CPU fallback")
+    ref = np.ascontiguousarray(ref, dtype=np.uint64)
+    n_ref, K, W = ref.shape
+    if W % BBITS:
+        raise ValueError("W must be sketchsize64 * 14")
+    ss64 = W // BBITS
+    n_qry = 0
+    if qry is not None:
+        qry = np.ascontiguousarray(qry, dtype=np.uint64)
+        n_qry = qry.shape[0]
+        if qry.shape[1:] != ref.shape[1:]:
+            raise ValueError("query and reference sketches differ in k-mers or sketch size")
+    kmers_np = np.ascontiguousarray(kmers, dtype=np.int32)
+    total = num_rows(n_ref, None if qry is None else n_qry)
+    if row_end is None:
+        row_end = total
+    rows = row_end - row_begin
+    C_ = 0
+    if rand_table is not None:
+        rand_table = np.ascontiguousarray(rand_table, dtype=np.float32)
+        C_ = rand_table.shape[0]
+        ref_cluster = np.ascontiguousarray(ref_cluster, dtype=np.uint16)
+        if qry is not None:
+            qry_cluster = np.ascontiguousarray(qry_cluster, dtype=np.uint16)
+    if want_out and out is None:
+        if out_mode == OUT_DISTS:
+            out = np.empty((rows, 2), dtype=np.float32)
+        elif out_mode == OUT_JACCARD:
+            out = np.empty((rows, K), dtype=np.float32)
+        else:
+            out = np.empty((rows, K), dtype=np.uint32)
+    bnd = _boundary(boundary)
+    labels = np.empty(rows, dtype=np.int8) if bnd is not None else None
+    ndeg = C.c_int64(0)
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data
+
+    check(L.ppb_query_host(ptr(ref), n_ref, ptr(qry), n_qry, ptr(kmers_np), K, ss64, BBITS, ptr(rand_table), C_,
+                           ptr(ref_cluster) if rand_table is not None else None,
+                           ptr(qry_cluster) if (rand_table is not None and qry is not None) else None,
+                           row_begin, row_end, out_mode, ptr(out), C.byref(bnd) if bnd is not None else None,
+                           ptr(labels), C.byref(ndeg), device_id), "ppb_query_host")
+    return out, labels, int(ndeg.value)
+
+
+# --------------------------------------------------------------------------------------------
+# multi-GPU: static row shards, one all-gather
+# --------------------------------------------------------------------------------------------
+def shard_rows(total_rows: int, world_size: int, rank: int) -> Tuple[int, int, int]:
+    """Equal contiguous row slices (the last ones padded): returns ``(begin, end, slice_len)``.
+
+    Self mode rows are condensed-order, so a slice is a band of whole rows i plus two partial ones — load is
+    balanced by pair count.  Non-self rows are query-major, so a slice is a range of queries."""
+    slice_len = -(-total_rows // world_size) if total_rows else 0
+    b = min(total_rows, rank * slice_len)
+    e = min(total_rows, b + slice_len)
+    return b, e, slice_len
+
+
+def query_sharded(ref: PackedSketches, qry: Optional[PackedSketches], kmers, rand_table=None,
+                  out_mode: int = OUT_DISTS, group=None, gather: bool = True, _query_fn=None):
+    """Every rank holds the (replicated) sketches, computes its static row shard and — if ``gather`` — one
+    ``all_gather_into_tensor`` (NCCL over NVLink on GPUs) reassembles the full row-ordered result on every
+    rank.  Returns ``(out, n_degenerate_total)``; without ``gather`` ``out`` is the local shard."""
+    import torch.distributed as dist
+    run = _query_fn or query   # tests substitute a CPU stand-in to exercise the sharding/gather logic
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    total = num_rows(ref.n, None if qry is None else qry.n)
+    b, e, slice_len = shard_rows(total, world, rank)
+    width = 2 if out_mode == OUT_DISTS else ref.K
+    dtype = torch.int32 if out_mode == OUT_COUNTS else torch.float32
+    if world == 1 or not gather:
+        out, _, ndeg = run(ref, qry, kmers, rand_table, b, e, out_mode)
+        if world > 1:
+            dist.all_reduce(ndeg, group=group)
+        return out, ndeg
+    full = torch.empty((world * slice_len, width), dtype=dtype, device=ref.device)
+    mine = full[rank * slice_len:(rank + 1) * slice_len]
+    _, _, ndeg = run(ref, qry, kmers, rand_table, b, e, out_mode, out=mine[:e - b])
+    dist.all_gather_into_tensor(full, mine, group=group)
+    dist.all_reduce(ndeg, group=group)
+    return full[:total], ndeg

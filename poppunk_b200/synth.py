@@ -116,3 +116,39 @@ def random_match_table(kmers, n_clusters=3, genome_length=2.1e6, seed=42):
 def synth_clusters(n, n_clusters=3, seed=42) -> np.ndarray:
     rng = np.random.default_rng(seed + 1)
     return rng.integers(0, n_clusters, size=n).astype(np.uint16)
+
+
+def synth_sketches_torch(n, kmers, sketchsize64, seed=42, device="cuda", n_lineages=8,
+                         pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=4096):
+    """Same population model as :func:`synth_sketches`, generated on ``device`` with torch (fast enough for
+    N = 100k).  Not bit-identical to the NumPy generator (different RNG) — bench.py uses it and hands the CPU
+    baseline a device->host copy of the very same array.  Returns int64 ``[n][K][W]`` (uint64 bit patterns)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    K, S = len(kmers), 64 * sketchsize64
+    km = torch.tensor(np.asarray(kmers, dtype=np.float64), device=dev)
+
+    def p_keep(m):
+        pi = torch.empty(m, device=dev, dtype=torch.float64).uniform_(*pi_range, generator=g)
+        a = torch.empty(m, device=dev, dtype=torch.float64).uniform_(*a_range, generator=g)
+        return torch.sqrt((1.0 - a)[:, None] * (1.0 - pi)[:, None] ** km[None, :]).float()
+
+    def derive(parent, p):
+        keep = torch.rand(parent.shape, device=dev, generator=g) < p[..., None]
+        fresh = torch.randint(0, 1 << BBITS, parent.shape, device=dev, dtype=torch.int16, generator=g)
+        return torch.where(keep, parent, fresh)
+
+    root = torch.randint(0, 1 << BBITS, (K, S), device=dev, dtype=torch.int16, generator=g)
+    lin = derive(root.expand(n_lineages, K, S), p_keep(n_lineages))
+    weights = (torch.ones(64, dtype=torch.int64, device=dev) << torch.arange(64, device=dev))  # bin t -> bit t
+    out = torch.empty((n, K, sketchsize64 * BBITS), dtype=torch.int64, device=dev)
+    for start in range(0, n, chunk):
+        m = min(chunk, n - start)
+        which = torch.randint(0, n_lineages, (m,), device=dev, generator=g)
+        sig = derive(lin[which], p_keep(m)).to(torch.int64).view(m, K, sketchsize64, 64)
+        dst = out[start:start + m].view(m, K, sketchsize64, BBITS)
+        for b in range(BBITS):
+            dst[..., b] = (((sig >> b) & 1) * weights).sum(dim=-1)
+    return out

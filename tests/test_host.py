@@ -1,0 +1,165 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/ppb.h declares, its host-only
+entry points agree with the oracle, the host logic (sharding, DB reading, error conventions) behaves like the
+reference, and the product path fails loudly without a CUDA device."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from poppunk_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KMERS = np.array([15, 19, 23, 27, 31], dtype=np.int32)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from poppunk_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from poppunk_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ppb.h")).read()
+    declared = set(re.findall(r"\b(ppb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ppb_version() == 100
+
+
+def test_abi_index_maps_match_oracle(lib, oracle):
+    for n in (2, 5, 64, 1001, 100_000):
+        total = n * (n - 1) // 2
+        for k in {0, 1, n - 2, n - 1, total // 3, total // 2, total - 2, total - 1} - {-1}:
+            if not 0 <= k < total:
+                continue
+            i = lib.ppb_calc_row_idx(k, n)
+            j = lib.ppb_calc_col_idx(k, i, n)
+            assert (i, j) == (oracle.calc_row_idx(k, n), oracle.calc_col_idx(k, i, n))
+            assert lib.ppb_square_to_condensed(i, j, n) == k
+    assert lib.ppb_num_rows(100_000, 0, 1) == 4_999_950_000
+    assert lib.ppb_num_rows(50_000, 1_000_000, 0) == 50_000_000_000
+    # packed size: K * ceil(2*ss64/32) slices * n padded to 128 * 1792 B
+    assert lib.ppb_packed_bytes(1000, 5, 16) == 5 * 1 * 1024 * 1792
+    assert lib.ppb_packed_bytes(10, 6, 156) == 6 * 10 * 128 * 1792
+
+
+def test_argument_errors_without_gpu(lib):
+    from poppunk_b200._lib import OUT_DISTS
+    k = KMERS.copy()
+    ref = synth.synth_sketches(4, KMERS, 2)
+    out = np.empty((6, 2), dtype=np.float32)
+    rc = lib.ppb_query_host(ref.ctypes.data, 4, None, 0, k.ctypes.data, 5, 2, 13, None, 0, None, None, 0, 6,
+                            OUT_DISTS, out.ctypes.data, None, None, None, 0)
+    assert rc == 1 and b"bbits" in lib.ppb_last_error()
+    rc = lib.ppb_query_host(ref.ctypes.data, 4, None, 0, k.ctypes.data, 5, 2, 14, None, 0, None, None, 0, 7,
+                            OUT_DISTS, out.ctypes.data, None, None, None, 0)
+    assert rc == 1 and b"row range" in lib.ppb_last_error()
+
+
+def test_fails_loudly_without_cuda(lib):
+    """No CPU fallback: on a box without a GPU every compute entry raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from poppunk_b200 import engine, refine
+    ref = synth.synth_sketches(4, KMERS, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.query_host(ref, None, KMERS)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.pack(ref)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        refine.assignThreshold(np.zeros((3, 2), dtype=np.float32), 2, 0.5, 0.5)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "poppunk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "libppo" not in txt and "ppo_" not in txt and "import oracle" not in txt, f
+
+
+def test_shard_rows():
+    from poppunk_b200.engine import shard_rows, num_rows
+    total = num_rows(100_000)
+    for world in (1, 2, 4, 8):
+        spans = [shard_rows(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert len({s[2] for s in spans}) == 1 and spans[0][2] * world >= total
+    assert shard_rows(5, 8, 7) == (5, 5, 1) and shard_rows(0, 4, 2) == (0, 0, 0)
+    assert num_rows(50_000, 1_000_000) == 50_000_000_000
+
+
+def test_dropin_error_conventions(tmp_path, lib):
+    """PopPUNK/sketchlib.py:523-524 (RuntimeError) and :575-580 (message + sys.exit(1))."""
+    from poppunk_b200 import sketchlib
+    names = [f"g{i}" for i in range(6)]
+    sk = synth.synth_sketches(6, KMERS, 2)
+    p = str(tmp_path / "db")
+    sketchlib.write_db_npz(p, names, KMERS, sk)
+    with pytest.raises(RuntimeError, match="Must use same db for self query"):
+        sketchlib.queryDatabase(names, names, p, str(tmp_path / "other"), KMERS, self=True)
+    with pytest.raises(SystemExit) as e:
+        sketchlib.queryDatabase(names, names[2:4], p, p, KMERS, self=False)
+    assert e.value.code == 1
+    db = sketchlib.read_db(p)
+    assert db.names == names and (db.kmers == KMERS).all() and db.sketchsize64 == 2 and db.bbits == 14
+    assert (db.index_of(["g4", "g0"]) == [4, 0]).all() and (db.k_index([19, 31]) == [1, 4]).all()
+    with pytest.raises(RuntimeError, match="not found"):
+        db.index_of(["nope"])
+    with pytest.raises(RuntimeError, match="k-mer length 21"):
+        db.k_index([21])
+    kmers, ss, codon = sketchlib.readDBParams(p)
+    assert (kmers == KMERS).all() and ss == 2 and codon is False
+    assert sketchlib.getSeqsInDb(p) == names
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    """world_size-2 CPU check of the N>1 path: static row shards + one all_gather_into_tensor reassemble
+    exactly the single-process result.  The per-shard compute is the oracle here (no GPU)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    from poppunk_b200 import engine
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ref = synth.synth_sketches(61, KMERS, 4, seed=3)
+        qry = synth.synth_sketches(9, KMERS, 4, seed=3, sample_seed=1)
+
+        def oracle_query(r, q, kmers, rand_table, b, e, out_mode, out=None):
+            res, ndeg = oracle.query(r, q, kmers, row_begin=b, row_end=e, out_mode=out_mode, threads=1)
+            t = torch.from_numpy(res.view(np.int32) if res.dtype == np.uint32 else res)
+            if out is not None:
+                out.copy_(t)
+            return (out if out is not None else t), None, torch.tensor([ndeg], dtype=torch.int64)
+
+        class Host:  # stands in for PackedSketches on a CPU box
+            def __init__(self, a):
+                self.a, self.n, self.K, self.device = a, a.shape[0], a.shape[1], torch.device("cpu")
+
+        for q in (None, qry):
+            full, ndeg = engine.query_sharded(Host(ref), None if q is None else Host(q), KMERS,
+                                              _query_fn=lambda r, qq, *a, **k: oracle_query(
+                                                  r.a, None if qq is None else qq.a, *a, **k))
+            exp, ndeg_o = oracle.query(ref, q, KMERS, threads=1)
+            assert full.shape == exp.shape and (full.numpy() == exp).all(), rank
+            assert int(ndeg.item()) == ndeg_o
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_allgather_gloo_world2(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
