@@ -242,7 +242,7 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     int tj = ppb::kMaxTJ;
     auto smem_need = [&](int tjv) {
         return (size_t)ppb::kStages * ppb::kStageBytes + (((size_t)K * tjv * ppb::kCntRowWords * 4 + 15) & ~(size_t)15) +
-               2 * ppb::kStages * sizeof(uint64_t);
+               2 * ppb::kStages * sizeof(uint64_t) + ppb::kComputeWarps * 16;
     };
     while (tj > ppb::kJB && smem_need(tj) > (size_t)max_smem) tj >>= 1;
     if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
@@ -265,15 +265,35 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     int sms = 0;
     if (int rc = num_sms(dev, &sms)) return rc;
     const size_t smem = smem_need(tj);
+    const bool single = p.n_slices == 1;
     static std::mutex attr_mu;
     {
         std::lock_guard<std::mutex> lk(attr_mu);
-        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    }
+    // y-table for the fused fit (stream-ordered scratch; skipped when it would be unreasonably large)
+    double *d_ytab = nullptr;
+    if (out_mode == PPB_OUT_DISTS) {
+        const size_t entries = (size_t)(d_rand_table ? (size_t)n_clusters * n_clusters : 1) * K * ((size_t)p.S + 1);
+        if (entries * sizeof(double) <= ((size_t)64 << 20)) {
+            PPB_CUDA(cudaMallocAsync(&d_ytab, entries * sizeof(double), st));
+            const int threads = 256;
+            const unsigned blocks = (unsigned)std::min<size_t>((entries + threads - 1) / threads, (size_t)sms * 8);
+            ppb::ytab_kernel<<<blocks, threads, 0, st>>>(p, d_ytab);
+            g_launches++;
+            PPB_CUDA(cudaGetLastError());
+            p.ytab = d_ytab;
+        }
     }
     const unsigned grid = (unsigned)std::min<int64_t>(tl.n, sms);
-    ppb::query_kernel<<<grid, ppb::kThreads, smem, st>>>(p);
+    if (single)
+        ppb::query_kernel<true><<<grid, ppb::kThreads, smem, st>>>(p);
+    else
+        ppb::query_kernel<false><<<grid, ppb::kThreads, smem, st>>>(p);
     g_launches++;
     PPB_CUDA(cudaGetLastError());
+    if (d_ytab) PPB_CUDA(cudaFreeAsync(d_ytab, st));
     return PPB_OK;
 }
 

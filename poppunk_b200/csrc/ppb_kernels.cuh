@@ -63,6 +63,7 @@ struct QueryParams {
     int32_t C;
     const uint16_t *clA, *clB;
     unsigned long long *n_degenerate;
+    const double *ytab;  // y-table (see ytab_kernel) or nullptr: compute logs in place
     double S, inv_S, tol;
     int32_t S_pow2;
     double x[PPB_MAX_K];
@@ -134,6 +135,38 @@ __global__ void threshold_kernel(const float2 *__restrict__ d, int64_t n, int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// y-table: y(c) = ln( max(0, c/S - r) / (1 - r) ) for every count c in [0, S], every k and every
+// (ref cluster, query cluster) pair — the only transcendental of the per-pair fit becomes one cached
+// 8-byte load.  Entries with J < 5/S hold the sentinel +1 (ln J <= 0 always), which ends the series.
+// Layout: double [max(C,1)^2][K][S + 1].
+// ------------------------------------------------------------------------------------------------
+constexpr double kYSentinel = 1.0;
+
+__device__ __forceinline__ double jaccard_of_count(const QueryParams &p, double c, const float *rt, int t) {
+    double jac = p.S_pow2 ? c * p.inv_S : c / p.S;
+    if (rt) {  // observed_excess(obs, r, 1): max(0, obs - r) / (1 - r)
+        const double r = (double)__ldg(rt + t);
+        double diff = jac - r;
+        if (diff < 0.0) diff = 0.0;
+        jac = diff / (1.0 - r);
+    }
+    return jac;
+}
+
+__global__ void ytab_kernel(const QueryParams p, double *__restrict__ ytab) {
+    const int S1 = (int)p.S + 1;
+    const int64_t per_cp = (int64_t)p.K * S1;
+    const int64_t total = per_cp * (p.rand_table ? (int64_t)p.C * p.C : 1);
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cp = o / per_cp;
+        const int t = (int)((o - cp * per_cp) / S1), c = (int)(o % S1);
+        const float *rt = p.rand_table ? p.rand_table + cp * p.K : nullptr;
+        const double jac = jaccard_of_count(p, (double)c, rt, t);
+        ytab[o] = jac < p.tol ? kYSentinel : log(jac);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-pair epilogue: counts (shared memory) -> Jaccard -> truncated log-linear fit -> outputs.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int tj, int jl, int il) {
@@ -141,6 +174,46 @@ __device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int t
     return (il & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
+__device__ __forceinline__ void finish_pair(const QueryParams &p, double sy, double sxy, int n, int64_t row,
+                                            bool &degenerate) {
+    float core = 0.0f, acc = 0.0f;
+    if (n < 2) {
+        degenerate = true;  // D3: fewer than two usable k -> (0, 0), counted
+    } else {
+        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
+        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];     // intercept = log(1 - acc)
+        core = beta < 0.0 ? (float)(1.0 - exp(beta)) : 0.0f;
+        acc = alpha < 0.0 ? (float)(1.0 - exp(alpha)) : 0.0f;
+    }
+    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    if (p.has_boundary) {
+        // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
+        const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
+        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
+    }
+}
+
+// fast path (PPB_OUT_DISTS with a y-table): K cached loads + a handful of DFMA per pair
+__device__ __forceinline__ void pair_epilogue_tab(const QueryParams &p, const uint32_t *cnt, int jl, int il,
+                                                  int64_t i, int64_t j, int64_t row, bool &degenerate) {
+    const int K = p.K, S1 = (int)p.S + 1;
+    const double *yt = p.ytab;
+    if (p.rand_table) yt += ((int64_t)p.clB[j] * p.C + p.clA[i]) * ((int64_t)K * S1);
+    double sy = 0.0, sxy = 0.0;
+    int n = 0;
+    bool open = true;
+    for (int t = 0; t < K; t++) {
+        const double y = __ldg(yt + t * S1 + read_count(cnt, t, p.tj, jl, il));
+        open = open && (y <= 0.0);  // the first k with J < 5/S ends the series (docs/sketching.rst:161-165)
+        const double ym = open ? y : 0.0;
+        sy += ym;
+        sxy = fma(p.x[t], ym, sxy);
+        n += open ? 1 : 0;
+    }
+    finish_pair(p, sy, sxy, n, row, degenerate);
+}
+
+// generic path: any output mode, logs computed in place (also the fallback when the y-table would be huge)
 __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32_t *cnt, int jl, int il,
                                               int64_t i, int64_t j, int64_t row, bool &degenerate) {
     const int K = p.K;
@@ -156,51 +229,62 @@ __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32
     int n = 0;
     bool open = true;
     for (int t = 0; t < K; t++) {
-        const double c = (double)read_count(cnt, t, p.tj, jl, il);
-        double jac = p.S_pow2 ? c * p.inv_S : c / p.S;
-        if (rt) {  // observed_excess(obs, r, 1): max(0, obs - r) / (1 - r)
-            const double r = (double)__ldg(rt + t);
-            double diff = jac - r;
-            if (diff < 0.0) diff = 0.0;
-            jac = diff / (1.0 - r);
-        }
+        const double jac = jaccard_of_count(p, (double)read_count(cnt, t, p.tj, jl, il), rt, t);
         if (p.out_mode == PPB_OUT_JACCARD) {
             reinterpret_cast<float *>(p.out)[row * K + t] = (float)jac;
             continue;
         }
         if (open) {
             if (jac < p.tol) {
-                open = false;  // this k and every larger one are ignored (docs/sketching.rst:161-165)
+                open = false;
             } else {
                 const double y = log(jac);
                 sy += y;
-                sxy += p.x[t] * y;
+                sxy = fma(p.x[t], y, sxy);
                 n++;
             }
         }
     }
     if (p.out_mode == PPB_OUT_JACCARD) return;
-
-    float core = 0.0f, acc = 0.0f;
-    if (n < 2) {
-        degenerate = true;
-    } else {
-        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
-        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];     // intercept = log(1 - acc)
-        core = beta < 0.0 ? (float)(1.0 - exp(beta)) : 0.0f;
-        acc = alpha < 0.0 ? (float)(1.0 - exp(alpha)) : 0.0f;
-    }
-    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
-    if (p.has_boundary) {
-        // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
-        const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
-        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
-    }
+    finish_pair(p, sy, sxy, n, row, degenerate);
 }
 
 // ------------------------------------------------------------------------------------------------
 // The hot path.  Persistent CTAs (one per SM), 8 compute warps + 1 TMA producer warp.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t redux_add(uint32_t v) {
+    uint32_t r;
+    asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack2(uint32_t lo, uint32_t hi) {  // lo + hi * 65536 on the FMA pipe (IMAD)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
+// lane 0 stores (or adds) this warp's 8 uint16 counts of one column: one predicated 16-byte shared store
+template <bool kAccumulate>
+__device__ __forceinline__ void store_counts(uint32_t dst, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3,
+                                             uint32_t lane, uint32_t accumulate) {
+    if (kAccumulate) {
+        if (lane == 0) {
+            if (accumulate) {
+                uint32_t o0, o1, o2, o3;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(dst));
+                r0 += o0, r1 += o1, r2 += o2, r3 += o3;
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+        }
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(dst),
+            "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(lane)
+            : "memory");
+    }
+}
+
+// kSingleSlice: S <= 1024 (one 32-group slice per k) — the common case; drops the accumulate path.
+template <bool kSingleSlice>
 __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constant__ QueryParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *stage_base = smem;
@@ -208,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
     const int cnt_words = p.K * p.tj * kCntRowWords;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + ((cnt_words * 4 + 15) & ~15));
     uint64_t *empty = full + kStages;
+    uint32_t *trash = reinterpret_cast<uint32_t *>(empty + kStages);  // 8 x 16 B: sink of the pipeline's first store
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -244,15 +329,22 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
     }
 
     // ===== compute warps =====
+    // Software pipeline over columns: while the LOP3 stream of column c runs, the packed partial counts of
+    // column c-1 go through REDUX and are stored at the end — no POPC/REDUX latency is ever waited for.
+    const uint32_t trash_addr = smem_u32(trash + warp * 4);
+    const uint32_t cnt_addr = smem_u32(cnt) + warp * (kRowsPerWarp / 2) * 4;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int2 tc = p.tiles[tile];
         const int64_t i0 = (int64_t)tc.x * kTI, j0 = (int64_t)tc.y * tj;
 
+        uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;  // packed (2 x uint16) partial counts of the previous column
+        uint32_t pdst = trash_addr, pacc = 0;          // where they go; whether they add to an earlier slice
+
         for (int ks = 0; ks < KS; ks++) {
-            const int k = ks / p.n_slices, sl = ks - k * p.n_slices;
+            const int k = kSingleSlice ? ks : ks / p.n_slices;
+            const int sl = kSingleSlice ? 0 : ks - k * p.n_slices;
             const uint32_t valid = (sl * 32 + lane < p.G32) ? 0xffffffffu : 0u;
-            const bool accumulate = sl != 0;  // later slices of the same k add to the stored counts
 
             // register-stationary row genomes: 8 x 14 plane words of this lane's group
             uint32_t a[kRowsPerWarp][kBbits];
@@ -269,55 +361,58 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
                     a[g][12] = v3.x, a[g][13] = v3.y;
                 }
             }
-            uint32_t *cnt_k = cnt + k * tj * kCntRowWords + warp * (kRowsPerWarp / 2);
+            const uint32_t cnt_k = cnt_addr + k * tj * kCntRowWords * 4;
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
+                uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
 #pragma unroll 2
-                for (int jj = 0; jj < kJB; jj++) {
+                for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];
                     uint32_t c[kRowsPerWarp];
-#pragma unroll
-                    for (int g = 0; g < kRowsPerWarp; g++) {
-                        uint32_t bits = valid;
-                        bits = and_xnor(bits, a[g][0], b0.x);
-                        bits = and_xnor(bits, a[g][1], b0.y);
-                        bits = and_xnor(bits, a[g][2], b0.z);
-                        bits = and_xnor(bits, a[g][3], b0.w);
-                        bits = and_xnor(bits, a[g][4], b1.x);
-                        bits = and_xnor(bits, a[g][5], b1.y);
-                        bits = and_xnor(bits, a[g][6], b1.z);
-                        bits = and_xnor(bits, a[g][7], b1.w);
-                        bits = and_xnor(bits, a[g][8], b2.x);
-                        bits = and_xnor(bits, a[g][9], b2.y);
-                        bits = and_xnor(bits, a[g][10], b2.z);
-                        bits = and_xnor(bits, a[g][11], b2.w);
-                        bits = and_xnor(bits, a[g][12], b3.x);
-                        bits = and_xnor(bits, a[g][13], b3.y);
-                        c[g] = __popc(bits);
-                    }
+#define PPB_CHAIN(g)                                   \
+    {                                                  \
+        uint32_t bits = valid;                         \
+        bits = and_xnor(bits, a[g][0], b0.x);          \
+        bits = and_xnor(bits, a[g][1], b0.y);          \
+        bits = and_xnor(bits, a[g][2], b0.z);          \
+        bits = and_xnor(bits, a[g][3], b0.w);          \
+        bits = and_xnor(bits, a[g][4], b1.x);          \
+        bits = and_xnor(bits, a[g][5], b1.y);          \
+        bits = and_xnor(bits, a[g][6], b1.z);          \
+        bits = and_xnor(bits, a[g][7], b1.w);          \
+        bits = and_xnor(bits, a[g][8], b2.x);          \
+        bits = and_xnor(bits, a[g][9], b2.y);          \
+        bits = and_xnor(bits, a[g][10], b2.z);         \
+        bits = and_xnor(bits, a[g][11], b2.w);         \
+        bits = and_xnor(bits, a[g][12], b3.x);         \
+        bits = and_xnor(bits, a[g][13], b3.y);         \
+        c[g] = __popc(bits);                           \
+    }
+                    // first half of this column's chains
+                    PPB_CHAIN(0) PPB_CHAIN(1) PPB_CHAIN(2) PPB_CHAIN(3)
+                    // previous column: warp-sum of its packed counts (inputs were ready an iteration ago)
+                    const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
+                    // second half
+                    PPB_CHAIN(4) PPB_CHAIN(5) PPB_CHAIN(6) PPB_CHAIN(7)
+#undef PPB_CHAIN
+                    store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
                     // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
-                    const uint32_t r0 = __reduce_add_sync(0xffffffffu, c[0] + (c[1] << 16));
-                    const uint32_t r1 = __reduce_add_sync(0xffffffffu, c[2] + (c[3] << 16));
-                    const uint32_t r2 = __reduce_add_sync(0xffffffffu, c[4] + (c[5] << 16));
-                    const uint32_t r3 = __reduce_add_sync(0xffffffffu, c[6] + (c[7] << 16));
-                    if (lane == 0) {  // one STS.128: this warp's 8 counts of column (jb, jj)
-                        uint4 *dst = reinterpret_cast<uint4 *>(cnt_k + (jb * kJB + jj) * kCntRowWords);
-                        uint4 v = make_uint4(r0, r1, r2, r3);
-                        if (accumulate) {
-                            const uint4 o = *dst;
-                            v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
-                        }
-                        *dst = v;
-                    }
+                    pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]), pk2 = pack2(c[4], c[5]), pk3 = pack2(c[6], c[7]);
+                    pdst = dst;
+                    pacc = sl;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
+        }
+        {  // drain the pipeline: the tile's last column
+            const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
+            store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
         }
         bar_sync(1, kComputeWarps * 32);  // every warp's counts for every k are in shared memory
 
@@ -325,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
         {
             const int tid = threadIdx.x;
             const int tj_shift = 31 - __clz(tj);
-            bool degenerate_any = false;
+            const bool fast = p.ytab != nullptr;
             for (int pi = tid; pi < kTI * tj; pi += kComputeWarps * 32) {
                 const int jl = pi & (tj - 1), il = pi >> tj_shift;
                 const int64_t i = i0 + il, j = j0 + jl;
@@ -340,14 +435,17 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
                 }
                 ok = ok && row >= p.row_begin && row < p.row_end;
                 bool deg = false;
-                if (ok) pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
-                degenerate_any |= deg;
+                if (ok) {
+                    if (fast)
+                        pair_epilogue_tab(p, cnt, jl, il, i, j, row - p.row_begin, deg);
+                    else
+                        pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
+                }
                 if (p.n_degenerate) {
                     const uint32_t m = __ballot_sync(0xffffffffu, deg);
                     if (m && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)__popc(m));
                 }
             }
-            (void)degenerate_any;
         }
         bar_sync(1, kComputeWarps * 32);  // counts consumed before the next tile overwrites them
     }
