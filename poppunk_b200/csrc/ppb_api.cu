@@ -48,10 +48,10 @@ inline int64_t col_idx(int64_t k, int64_t i, int64_t n) {
 }
 
 // ---- tile schedule -----------------------------------------------------------------------
-// Tiles are (64 rows) x (tj columns).  Order: bands of kBand row-tiles; inside a band the column tile is
+// Tiles are (kTI rows) x (tj columns).  Order: bands of kBand row-tiles; inside a band the column tile is
 // the slow index, so the CTAs running at any moment share a handful of column tiles (L2 hits) and the
 // band's row genomes stay L2-resident while the columns stream past once per band.
-constexpr int kBand = 32;
+constexpr int kBand = 64;
 
 struct TileKey {
     int dev;
@@ -237,14 +237,16 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     }
 
     // column-tile width: the widest whose uint16 count buffer fits beside the TMA ring
-    int max_smem = 0;
+    int max_smem = 0, sm_smem = 0;
     PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int tj = ppb::kMaxTJ;
+    PPB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     auto smem_need = [&](int tjv) {
         return (size_t)ppb::kStages * ppb::kStageBytes + (((size_t)K * tjv * ppb::kCntRowWords * 4 + 15) & ~(size_t)15) +
                2 * ppb::kStages * sizeof(uint64_t) + ppb::kComputeWarps * 16;
     };
-    while (tj > ppb::kJB && smem_need(tj) > (size_t)max_smem) tj >>= 1;
+    const size_t per_cta_budget = std::min<size_t>((size_t)max_smem, (size_t)sm_smem / ppb::kCtasPerSM - 1024);
+    int tj = ppb::kMaxTJ;
+    while (tj > ppb::kJB && smem_need(tj) > per_cta_budget) tj >>= 1;
     if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
     p.tj = tj;
 
@@ -271,6 +273,8 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
         std::lock_guard<std::mutex> lk(attr_mu);
         PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     // y-table for the fused fit (stream-ordered scratch; skipped when it would be unreasonably large)
     double *d_ytab = nullptr;
@@ -286,7 +290,7 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
             p.ytab = d_ytab;
         }
     }
-    const unsigned grid = (unsigned)std::min<int64_t>(tl.n, sms);
+    const unsigned grid = (unsigned)std::min<int64_t>(tl.n, (int64_t)ppb::kCtasPerSM * sms);
     if (single)
         ppb::query_kernel<true><<<grid, ppb::kThreads, smem, st>>>(p);
     else

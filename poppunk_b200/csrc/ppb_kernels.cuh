@@ -44,6 +44,7 @@ constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: ro
 constexpr int kThreads = (kComputeWarps + 1) * 32; // + 1 TMA producer warp
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
+constexpr int kCtasPerSM = 1;                      // measured: 2 x (4 warps, 32-row tiles) is slower (profiles/)
 
 struct QueryParams {
     const uint32_t *A;  // packed rows   (queries; == B in self mode)
@@ -193,24 +194,115 @@ __device__ __forceinline__ void finish_pair(const QueryParams &p, double sy, dou
     }
 }
 
-// fast path (PPB_OUT_DISTS with a y-table): K cached loads + a handful of DFMA per pair
-__device__ __forceinline__ void pair_epilogue_tab(const QueryParams &p, const uint32_t *cnt, int jl, int il,
-                                                  int64_t i, int64_t j, int64_t row, bool &degenerate) {
-    const int K = p.K, S1 = (int)p.S + 1;
-    const double *yt = p.ytab;
-    if (p.rand_table) yt += ((int64_t)p.clB[j] * p.C + p.clA[i]) * ((int64_t)K * S1);
-    double sy = 0.0, sxy = 0.0;
-    int n = 0;
-    bool open = true;
-    for (int t = 0; t < K; t++) {
-        const double y = __ldg(yt + t * S1 + read_count(cnt, t, p.tj, jl, il));
-        open = open && (y <= 0.0);  // the first k with J < 5/S ends the series (docs/sketching.rst:161-165)
-        const double ym = open ? y : 0.0;
-        sy += ym;
-        sxy = fma(p.x[t], ym, sxy);
-        n += open ? 1 : 0;
+// exp(x) for x <= 0 in float64 without the special-case handling of the library version: Cody-Waite
+// reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), exponent insert.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -700.0);
+    const int n = __double2int_rn(x * 1.4426950408889634);
+    const double fn = (double)n;
+    double r = fma(-fn, 6.93147180369123816490e-01, x);
+    r = fma(-fn, 1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;                 // 1/13!
+    q = fma(q, r, 2.08767569878681e-09);               // 1/12!
+    q = fma(q, r, 2.505210838544172e-08);              // 1/11!
+    q = fma(q, r, 2.755731922398589e-07);              // 1/10!
+    q = fma(q, r, 2.7557319223985893e-06);             // 1/9!
+    q = fma(q, r, 2.48015873015873e-05);               // 1/8!
+    q = fma(q, r, 1.984126984126984e-04);              // 1/7!
+    q = fma(q, r, 1.388888888888889e-03);              // 1/6!
+    q = fma(q, r, 8.333333333333333e-03);              // 1/5!
+    q = fma(q, r, 4.1666666666666664e-02);             // 1/4!
+    q = fma(q, r, 1.6666666666666666e-01);             // 1/3!
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    return q * __hiloint2double((n + 1023) << 20, 0);  // 2^n, n in [-1010, 0]
+}
+
+__device__ __forceinline__ void finish_pair_fast(const QueryParams &p, double sy, double sxy, int n, int64_t row,
+                                                 bool &degenerate) {
+    float core = 0.0f, acc = 0.0f;
+    if (n < 2) {
+        degenerate = true;  // D3
+    } else {
+        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];
+        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];
+        core = beta < 0.0 ? (float)(1.0 - exp_nonpos(beta)) : 0.0f;
+        acc = alpha < 0.0 ? (float)(1.0 - exp_nonpos(alpha)) : 0.0f;
     }
-    finish_pair(p, sy, sxy, n, row, degenerate);
+    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    if (p.has_boundary) {
+        const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
+        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
+    }
+}
+
+// fast path (PPB_OUT_DISTS with a y-table): kEpiPairs pairs of one column in flight per thread, so the
+// K table loads of each (L1/L2 hits) overlap instead of being waited for one at a time.
+constexpr int kEpiPairs = 4;
+
+__device__ __forceinline__ void epilogue_tab(const QueryParams &p, const uint32_t *cnt, int64_t i0, int64_t j0,
+                                             int tid, int lane) {
+    const int K = p.K, S1 = (int)p.S + 1, tj = p.tj;
+    const int tj_shift = 31 - __clz(tj);
+    const int jl = tid & (tj - 1), il_first = tid >> tj_shift, il_step = (kComputeWarps * 32) >> tj_shift;
+    const int64_t j = j0 + jl;
+    const uint16_t *cnt16 = reinterpret_cast<const uint16_t *>(cnt) + jl * (kCntRowWords * 2);
+    const int64_t cp_stride = (int64_t)K * S1;
+    const bool j_ok = j < p.nB;
+    const int64_t cpB = (p.rand_table && j_ok) ? (int64_t)p.clB[j] * p.C : 0;
+
+    for (int il_base = il_first; il_base < kTI; il_base += il_step * kEpiPairs) {
+        const double *yt[kEpiPairs];
+        int64_t row[kEpiPairs];
+        bool ok[kEpiPairs];
+        double sy[kEpiPairs], sxy[kEpiPairs];
+        int n[kEpiPairs];
+        bool open[kEpiPairs];
+#pragma unroll
+        for (int u = 0; u < kEpiPairs; u++) {
+            const int il = il_base + u * il_step;
+            const int64_t i = i0 + il;
+            if (p.self) {
+                ok[u] = (i < j) && j_ok;
+                row[u] = p.nB * i - ((i * (i + 1)) >> 1) + j - 1 - i;  // boundary.cpp:33-37
+            } else {
+                ok[u] = (i < p.nA) && j_ok;
+                row[u] = i * p.nB + j;  // utils.py:224-226
+            }
+            ok[u] = ok[u] && il < kTI && row[u] >= p.row_begin && row[u] < p.row_end;
+            yt[u] = p.ytab + ((p.rand_table && ok[u]) ? (cpB + p.clA[i]) * cp_stride : 0);
+            sy[u] = 0.0, sxy[u] = 0.0, n[u] = 0, open[u] = true;
+        }
+#pragma unroll 4
+        for (int t = 0; t < K; t++) {
+            const double x = p.x[t];
+#pragma unroll
+            for (int u = 0; u < kEpiPairs; u++) {
+                const int il = min(il_base + u * il_step, kTI - 1);
+                const uint32_t c = cnt16[t * tj * (kCntRowWords * 2) + il];
+                const double y = __ldg(yt[u] + t * S1 + c);
+                open[u] = open[u] && (y <= 0.0);  // the first k with J < 5/S ends the series
+                const double ym = open[u] ? y : 0.0;
+                sy[u] += ym;
+                sxy[u] = fma(x, ym, sxy[u]);
+                n[u] += open[u] ? 1 : 0;
+            }
+        }
+        bool deg = false;
+#pragma unroll
+        for (int u = 0; u < kEpiPairs; u++)
+            if (ok[u]) finish_pair_fast(p, sy[u], sxy[u], n[u], row[u] - p.row_begin, deg);
+        if (p.n_degenerate) {
+            // several of this thread's pairs may be degenerate: count them exactly
+            int nd = 0;
+#pragma unroll
+            for (int u = 0; u < kEpiPairs; u++) nd += (ok[u] && n[u] < 2) ? 1 : 0;
+            const uint32_t total = __reduce_add_sync(0xffffffffu, (uint32_t)nd);
+            if (total && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)total);
+        }
+        (void)deg;
+    }
 }
 
 // generic path: any output mode, logs computed in place (also the fallback when the y-table would be huge)
@@ -285,7 +377,7 @@ __device__ __forceinline__ void store_counts(uint32_t dst, uint32_t r0, uint32_t
 
 // kSingleSlice: S <= 1024 (one 32-group slice per k) — the common case; drops the accumulate path.
 template <bool kSingleSlice>
-__global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __grid_constant__ QueryParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *stage_base = smem;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes);
@@ -417,10 +509,11 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
         bar_sync(1, kComputeWarps * 32);  // every warp's counts for every k are in shared memory
 
         // ===== epilogue: consecutive lanes -> consecutive columns j -> coalesced row-order stores =====
-        {
+        if (p.ytab != nullptr) {
+            epilogue_tab(p, cnt, i0, j0, threadIdx.x, lane);
+        } else {
             const int tid = threadIdx.x;
             const int tj_shift = 31 - __clz(tj);
-            const bool fast = p.ytab != nullptr;
             for (int pi = tid; pi < kTI * tj; pi += kComputeWarps * 32) {
                 const int jl = pi & (tj - 1), il = pi >> tj_shift;
                 const int64_t i = i0 + il, j = j0 + jl;
@@ -435,12 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_kernel(const __grid_constan
                 }
                 ok = ok && row >= p.row_begin && row < p.row_end;
                 bool deg = false;
-                if (ok) {
-                    if (fast)
-                        pair_epilogue_tab(p, cnt, jl, il, i, j, row - p.row_begin, deg);
-                    else
-                        pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
-                }
+                if (ok) pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
                 if (p.n_degenerate) {
                     const uint32_t m = __ballot_sync(0xffffffffu, deg);
                     if (m && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)__popc(m));
