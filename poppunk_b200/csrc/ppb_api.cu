@@ -240,10 +240,7 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     int max_smem = 0, sm_smem = 0;
     PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     PPB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    auto smem_need = [&](int tjv) {
-        return (size_t)ppb::kStages * ppb::kStageBytes + (((size_t)K * tjv * ppb::kCntRowWords * 4 + 15) & ~(size_t)15) +
-               2 * ppb::kStages * sizeof(uint64_t) + ppb::kComputeWarps * 16;
-    };
+    auto smem_need = [&](int tjv) { return (size_t)ppb::smem_layout(K, tjv).total; };
     const size_t per_cta_budget = std::min<size_t>((size_t)max_smem, (size_t)sm_smem / ppb::kCtasPerSM - 1024);
     int tj = ppb::kMaxTJ;
     while (tj > ppb::kJB && smem_need(tj) > per_cta_budget) tj >>= 1;

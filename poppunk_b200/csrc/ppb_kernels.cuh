@@ -37,14 +37,16 @@ constexpr int kSliceBytes = kSliceWords * 4;  // 1792
 constexpr int kRowsPerWarp = 8;               // register-stationary genomes per warp
 constexpr int kComputeWarps = 8;
 constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
-constexpr int kJB = 16;                            // column genomes per pipeline stage
+constexpr int kJB = 8;                             // column genomes per pipeline stage
 constexpr int kStages = 3;
-constexpr int kStageBytes = kJB * kSliceBytes;     // 28672
+constexpr int kStageBytes = kJB * kSliceBytes;     // 14336
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
-constexpr int kThreads = (kComputeWarps + 1) * 32; // + 1 TMA producer warp
+constexpr int kEpiWarps = 3;                       // epilogue warps (fit + stores), off the LOP3 critical path
+constexpr int kThreads = (kComputeWarps + 1 + kEpiWarps) * 32;  // + 1 TMA producer warp
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
 constexpr int kCtasPerSM = 1;                      // measured: 2 x (4 warps, 32-row tiles) is slower (profiles/)
+constexpr int kCntBufs = 2;                        // count tiles: one being filled, one being fitted
 
 struct QueryParams {
     const uint32_t *A;  // packed rows   (queries; == B in self mode)
@@ -175,133 +177,47 @@ __device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int t
     return (il & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
-__device__ __forceinline__ void finish_pair(const QueryParams &p, double sy, double sxy, int n, int64_t row,
-                                            bool &degenerate) {
-    float core = 0.0f, acc = 0.0f;
-    if (n < 2) {
-        degenerate = true;  // D3: fewer than two usable k -> (0, 0), counted
-    } else {
-        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
-        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];     // intercept = log(1 - acc)
-        core = beta < 0.0 ? (float)(1.0 - exp(beta)) : 0.0f;
-        acc = alpha < 0.0 ? (float)(1.0 - exp(alpha)) : 0.0f;
-    }
-    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
-    if (p.has_boundary) {
-        // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
-        const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
-        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
-    }
-}
 
 // exp(x) for x <= 0 in float64 without the special-case handling of the library version: Cody-Waite
 // reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), exponent insert.
+__constant__ double kExpPoly[12] = {1.6059043836821613e-10, 2.08767569878681e-09,  2.505210838544172e-08,
+                                    2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
+                                    1.984126984126984e-04,  1.388888888888889e-03,  8.333333333333333e-03,
+                                    4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
 __device__ __forceinline__ double exp_nonpos(double x) {
     x = fmax(x, -700.0);
     const int n = __double2int_rn(x * 1.4426950408889634);
     const double fn = (double)n;
     double r = fma(-fn, 6.93147180369123816490e-01, x);
     r = fma(-fn, 1.90821492927058770002e-10, r);
-    double q = 1.6059043836821613e-10;                 // 1/13!
-    q = fma(q, r, 2.08767569878681e-09);               // 1/12!
-    q = fma(q, r, 2.505210838544172e-08);              // 1/11!
-    q = fma(q, r, 2.755731922398589e-07);              // 1/10!
-    q = fma(q, r, 2.7557319223985893e-06);             // 1/9!
-    q = fma(q, r, 2.48015873015873e-05);               // 1/8!
-    q = fma(q, r, 1.984126984126984e-04);              // 1/7!
-    q = fma(q, r, 1.388888888888889e-03);              // 1/6!
-    q = fma(q, r, 8.333333333333333e-03);              // 1/5!
-    q = fma(q, r, 4.1666666666666664e-02);             // 1/4!
-    q = fma(q, r, 1.6666666666666666e-01);             // 1/3!
-    q = fma(q, r, 0.5);
+    double q = kExpPoly[0];
+#pragma unroll
+    for (int d = 1; d < 12; d++) q = fma(q, r, kExpPoly[d]);
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);
     return q * __hiloint2double((n + 1023) << 20, 0);  // 2^n, n in [-1010, 0]
 }
 
-__device__ __forceinline__ void finish_pair_fast(const QueryParams &p, double sy, double sxy, int n, int64_t row,
-                                                 bool &degenerate) {
+// Per-row facts the epilogue warps precompute once per tile (shared memory).
+struct RowInfo {
+    long long row_base;  // output row of (i, j) is row_base + j   (already minus row_begin)
+    int32_t ytab_off;    // this row's cluster offset into the y-table (elements)
+    int32_t i_ok;        // row genome exists
+};
+
+__device__ __forceinline__ void store_pair(const QueryParams &p, double sy, double sxy, int n, long long row) {
     float core = 0.0f, acc = 0.0f;
-    if (n < 2) {
-        degenerate = true;  // D3
-    } else {
-        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];
-        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];
+    if (n >= 2) {
+        const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
+        const double alpha = sy * p.inv_n[n] - beta * p.xbar[n];     // intercept = log(1 - acc)
         core = beta < 0.0 ? (float)(1.0 - exp_nonpos(beta)) : 0.0f;
         acc = alpha < 0.0 ? (float)(1.0 - exp_nonpos(alpha)) : 0.0f;
-    }
+    }  // else D3: fewer than two usable k -> (0, 0), counted by the caller
     if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
     if (p.has_boundary) {
+        // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
         const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
         p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
-    }
-}
-
-// fast path (PPB_OUT_DISTS with a y-table): kEpiPairs pairs of one column in flight per thread, so the
-// K table loads of each (L1/L2 hits) overlap instead of being waited for one at a time.
-constexpr int kEpiPairs = 4;
-
-__device__ __forceinline__ void epilogue_tab(const QueryParams &p, const uint32_t *cnt, int64_t i0, int64_t j0,
-                                             int tid, int lane) {
-    const int K = p.K, S1 = (int)p.S + 1, tj = p.tj;
-    const int tj_shift = 31 - __clz(tj);
-    const int jl = tid & (tj - 1), il_first = tid >> tj_shift, il_step = (kComputeWarps * 32) >> tj_shift;
-    const int64_t j = j0 + jl;
-    const uint16_t *cnt16 = reinterpret_cast<const uint16_t *>(cnt) + jl * (kCntRowWords * 2);
-    const int64_t cp_stride = (int64_t)K * S1;
-    const bool j_ok = j < p.nB;
-    const int64_t cpB = (p.rand_table && j_ok) ? (int64_t)p.clB[j] * p.C : 0;
-
-    for (int il_base = il_first; il_base < kTI; il_base += il_step * kEpiPairs) {
-        const double *yt[kEpiPairs];
-        int64_t row[kEpiPairs];
-        bool ok[kEpiPairs];
-        double sy[kEpiPairs], sxy[kEpiPairs];
-        int n[kEpiPairs];
-        bool open[kEpiPairs];
-#pragma unroll
-        for (int u = 0; u < kEpiPairs; u++) {
-            const int il = il_base + u * il_step;
-            const int64_t i = i0 + il;
-            if (p.self) {
-                ok[u] = (i < j) && j_ok;
-                row[u] = p.nB * i - ((i * (i + 1)) >> 1) + j - 1 - i;  // boundary.cpp:33-37
-            } else {
-                ok[u] = (i < p.nA) && j_ok;
-                row[u] = i * p.nB + j;  // utils.py:224-226
-            }
-            ok[u] = ok[u] && il < kTI && row[u] >= p.row_begin && row[u] < p.row_end;
-            yt[u] = p.ytab + ((p.rand_table && ok[u]) ? (cpB + p.clA[i]) * cp_stride : 0);
-            sy[u] = 0.0, sxy[u] = 0.0, n[u] = 0, open[u] = true;
-        }
-#pragma unroll 4
-        for (int t = 0; t < K; t++) {
-            const double x = p.x[t];
-#pragma unroll
-            for (int u = 0; u < kEpiPairs; u++) {
-                const int il = min(il_base + u * il_step, kTI - 1);
-                const uint32_t c = cnt16[t * tj * (kCntRowWords * 2) + il];
-                const double y = __ldg(yt[u] + t * S1 + c);
-                open[u] = open[u] && (y <= 0.0);  // the first k with J < 5/S ends the series
-                const double ym = open[u] ? y : 0.0;
-                sy[u] += ym;
-                sxy[u] = fma(x, ym, sxy[u]);
-                n[u] += open[u] ? 1 : 0;
-            }
-        }
-        bool deg = false;
-#pragma unroll
-        for (int u = 0; u < kEpiPairs; u++)
-            if (ok[u]) finish_pair_fast(p, sy[u], sxy[u], n[u], row[u] - p.row_begin, deg);
-        if (p.n_degenerate) {
-            // several of this thread's pairs may be degenerate: count them exactly
-            int nd = 0;
-#pragma unroll
-            for (int u = 0; u < kEpiPairs; u++) nd += (ok[u] && n[u] < 2) ? 1 : 0;
-            const uint32_t total = __reduce_add_sync(0xffffffffu, (uint32_t)nd);
-            if (total && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)total);
-        }
-        (void)deg;
     }
 }
 
@@ -338,11 +254,95 @@ __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32
         }
     }
     if (p.out_mode == PPB_OUT_JACCARD) return;
-    finish_pair(p, sy, sxy, n, row, degenerate);
+    degenerate = n < 2;
+    store_pair(p, sy, sxy, n, row);
+}
+
+
+// Epilogue of one tile, run by the kEpiWarps epilogue warps (et = 0..95).  Work unit = 4 consecutive rows x
+// 32 column slots (lane = column: coalesced 256-B row-order stores); the 4 rows' counts of one k are one LDS.64.
+__device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32_t *cnt, RowInfo *rinfo, int64_t i0,
+                                              int64_t j0, int et, int lane) {
+    const int K = p.K, S1 = (int)p.S + 1, tj = p.tj;
+    const int tj_shift = 31 - __clz(tj);
+    // ---- per-row facts
+    for (int il = et; il < kTI; il += kEpiWarps * 32) {
+        const int64_t i = i0 + il;
+        RowInfo ri;
+        ri.i_ok = i < p.nA;
+        ri.row_base = (p.self ? p.nB * i - ((i * (i + 1)) >> 1) - 1 - i   // boundary.cpp:33-37
+                              : i * p.nB) - p.row_begin;                  // utils.py:224-226
+        ri.ytab_off = (p.rand_table && ri.i_ok) ? (int32_t)p.clA[i] * K * S1 : 0;
+        rinfo[il] = ri;
+    }
+    bar_sync(2, kEpiWarps * 32);
+    const int ewarp = et >> 5;
+    const int n_units = (kTI / 4) * tj / 32;
+    const bool fast = p.ytab != nullptr;
+    uint32_t n_deg = 0;
+    for (int u = ewarp; u < n_units; u += kEpiWarps) {
+        const int flat = u * 32 + lane;
+        const int jl = flat & (tj - 1), il0 = (flat >> tj_shift) * 4;
+        const int64_t j = j0 + jl;
+        const bool j_ok = j < p.nB;
+        const uint32_t *cnt_col = cnt + jl * kCntRowWords + (il0 >> 1);
+        if (fast) {
+            const int32_t col_off = (p.rand_table && j_ok) ? (int32_t)p.clB[j] * p.C * K * S1 : 0;
+            double sy[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
+            int n[4] = {0, 0, 0, 0};
+            bool open[4] = {true, true, true, true};
+            int32_t off[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) off[r] = col_off + rinfo[il0 + r].ytab_off;
+#pragma unroll 5
+            for (int t = 0; t < K; t++) {
+                const uint2 w = *reinterpret_cast<const uint2 *>(cnt_col + t * tj * kCntRowWords);
+                const uint32_t c[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+                const double x = p.x[t];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const double y = __ldg(p.ytab + (off[r] + t * S1 + (int32_t)c[r]));
+                    open[r] = open[r] && (y <= 0.0);  // the first k with J < 5/S ends the series
+                    const double ym = open[r] ? y : 0.0;
+                    sy[r] += ym;
+                    sxy[r] = fma(x, ym, sxy[r]);
+                    n[r] += open[r] ? 1 : 0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const RowInfo ri = rinfo[il0 + r];
+                const long long row = ri.row_base + j;
+                const bool ok = ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
+                                row < p.row_end - p.row_begin;
+                if (ok) {
+                    store_pair(p, sy[r], sxy[r], n[r], row);
+                    n_deg += n[r] < 2;
+                }
+            }
+        } else {
+            for (int r = 0; r < 4; r++) {
+                const RowInfo ri = rinfo[il0 + r];
+                const long long row = ri.row_base + j;
+                const bool ok = ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
+                                row < p.row_end - p.row_begin;
+                bool deg = false;
+                if (ok) pair_epilogue(p, cnt, jl, il0 + r, i0 + il0 + r, j, row, deg);
+                n_deg += deg;
+            }
+        }
+    }
+    if (p.n_degenerate) {
+        const uint32_t total = __reduce_add_sync(0xffffffffu, n_deg);
+        if (total && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)total);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// The hot path.  Persistent CTAs (one per SM), 8 compute warps + 1 TMA producer warp.
+// The hot path.  Persistent CTAs (one per SM), warp-specialised:
+//   warps 0-7   compute: LOP3/POPC/REDUX stream, never leave it (count tile double-buffered)
+//   warp  8     TMA producer: 1-D bulk copies of column-genome slices into a 3-stage ring
+//   warps 9-11  epilogue: counts -> fit -> row-ordered stores of the previous tile, concurrently
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t redux_add(uint32_t v) {
     uint32_t r;
@@ -375,22 +375,41 @@ __device__ __forceinline__ void store_counts(uint32_t dst, uint32_t r0, uint32_t
     }
 }
 
+struct SmemLayout {
+    uint32_t cnt_bytes;   // one count tile
+    uint32_t off_cnt, off_rinfo, off_bar, off_trash, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int K, int tj) {
+    SmemLayout L;
+    L.cnt_bytes = ((uint32_t)K * tj * kCntRowWords * 4 + 127u) & ~127u;
+    L.off_cnt = kStages * kStageBytes;
+    L.off_rinfo = L.off_cnt + kCntBufs * L.cnt_bytes;
+    L.off_bar = L.off_rinfo + kTI * (uint32_t)sizeof(RowInfo);
+    L.off_trash = L.off_bar + (2 * kStages + 2 * kCntBufs) * 8;
+    L.total = L.off_trash + kComputeWarps * 16;
+    return L;
+}
+
 // kSingleSlice: S <= 1024 (one 32-group slice per k) — the common case; drops the accumulate path.
 template <bool kSingleSlice>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __grid_constant__ QueryParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const SmemLayout L = smem_layout(p.K, p.tj);
     uint8_t *stage_base = smem;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes);
-    const int cnt_words = p.K * p.tj * kCntRowWords;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + ((cnt_words * 4 + 15) & ~15));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     uint64_t *empty = full + kStages;
-    uint32_t *trash = reinterpret_cast<uint32_t *>(empty + kStages);  // 8 x 16 B: sink of the pipeline's first store
+    uint64_t *cfull = empty + kStages;    // count tile b complete (all compute warps arrived)
+    uint64_t *cempty = cfull + kCntBufs;  // count tile b consumed (all epilogue warps arrived)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kComputeWarps);
+        }
+        for (int b = 0; b < kCntBufs; b++) {
+            mbar_init(&cfull[b], kComputeWarps);
+            mbar_init(&cempty[b], kEpiWarps);
         }
         mbar_fence_init();
     }
@@ -420,15 +439,35 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         return;
     }
 
+    if (warp > kComputeWarps) {
+        // ===== epilogue warps: fit + stores of tile t while the compute warps are already in tile t+1 =====
+        const int et = threadIdx.x - (kComputeWarps + 1) * 32;
+        RowInfo *rinfo = reinterpret_cast<RowInfo *>(smem + L.off_rinfo);
+        uint32_t lt = 0;
+        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
+            const int2 tc = p.tiles[tile];
+            const uint32_t b = lt % kCntBufs, ph = (lt / kCntBufs) & 1;
+            mbar_wait(&cfull[b], ph);
+            const uint32_t *cnt = reinterpret_cast<const uint32_t *>(smem + L.off_cnt + b * L.cnt_bytes);
+            tile_epilogue(p, cnt, rinfo, (int64_t)tc.x * kTI, (int64_t)tc.y * tj, et, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cempty[b]);
+            bar_sync(2, kEpiWarps * 32);  // rinfo is rewritten by the next tile
+        }
+        return;
+    }
+
     // ===== compute warps =====
     // Software pipeline over columns: while the LOP3 stream of column c runs, the packed partial counts of
     // column c-1 go through REDUX and are stored at the end — no POPC/REDUX latency is ever waited for.
-    const uint32_t trash_addr = smem_u32(trash + warp * 4);
-    const uint32_t cnt_addr = smem_u32(cnt) + warp * (kRowsPerWarp / 2) * 4;
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
+    uint32_t it = 0, lt = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
         const int2 tc = p.tiles[tile];
-        const int64_t i0 = (int64_t)tc.x * kTI, j0 = (int64_t)tc.y * tj;
+        const int64_t i0 = (int64_t)tc.x * kTI;
+        const uint32_t cb = lt % kCntBufs, cph = (lt / kCntBufs) & 1;
+        const uint32_t cnt_addr = smem_u32(smem + L.off_cnt + cb * L.cnt_bytes) + warp * (kRowsPerWarp / 2) * 4;
+        mbar_wait(&cempty[cb], cph ^ 1);  // the epilogue warps are done with this count tile (2 tiles ago)
 
         uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;  // packed (2 x uint16) partial counts of the previous column
         uint32_t pdst = trash_addr, pacc = 0;          // where they go; whether they add to an earlier slice
@@ -506,36 +545,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
             const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
             store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
         }
-        bar_sync(1, kComputeWarps * 32);  // every warp's counts for every k are in shared memory
-
-        // ===== epilogue: consecutive lanes -> consecutive columns j -> coalesced row-order stores =====
-        if (p.ytab != nullptr) {
-            epilogue_tab(p, cnt, i0, j0, threadIdx.x, lane);
-        } else {
-            const int tid = threadIdx.x;
-            const int tj_shift = 31 - __clz(tj);
-            for (int pi = tid; pi < kTI * tj; pi += kComputeWarps * 32) {
-                const int jl = pi & (tj - 1), il = pi >> tj_shift;
-                const int64_t i = i0 + il, j = j0 + jl;
-                bool ok;
-                int64_t row;
-                if (p.self) {
-                    ok = (i < j) && (j < p.nB);
-                    row = p.nB * i - ((i * (i + 1)) >> 1) + j - 1 - i;  // boundary.cpp:33-37
-                } else {
-                    ok = (i < p.nA) && (j < p.nB);
-                    row = i * p.nB + j;  // utils.py:224-226
-                }
-                ok = ok && row >= p.row_begin && row < p.row_end;
-                bool deg = false;
-                if (ok) pair_epilogue(p, cnt, jl, il, i, j, row - p.row_begin, deg);
-                if (p.n_degenerate) {
-                    const uint32_t m = __ballot_sync(0xffffffffu, deg);
-                    if (m && lane == 0) atomicAdd(p.n_degenerate, (unsigned long long)__popc(m));
-                }
-            }
-        }
-        bar_sync(1, kComputeWarps * 32);  // counts consumed before the next tile overwrites them
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cfull[cb]);  // release: this warp's counts of the tile are visible
     }
 }
 
