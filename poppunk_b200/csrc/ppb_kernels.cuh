@@ -41,7 +41,7 @@ constexpr int kJB = 8;                             // column genomes per pipelin
 constexpr int kStages = 3;
 constexpr int kStageBytes = kJB * kSliceBytes;     // 14336
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
-constexpr int kEpiWarps = 3;                       // epilogue warps (fit + stores), off the LOP3 critical path
+constexpr int kEpiWarps = 2;                       // epilogue warps (fit + stores), off the LOP3 critical path
 constexpr int kThreads = (kComputeWarps + 1 + kEpiWarps) * 32;  // + 1 TMA producer warp
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
@@ -499,38 +499,40 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
-#pragma unroll 2
+#pragma unroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];
+                    const uint32_t bw[kBbits] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z,
+                                                 b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y};
                     uint32_t c[kRowsPerWarp];
-#define PPB_CHAIN(g)                                   \
-    {                                                  \
-        uint32_t bits = valid;                         \
-        bits = and_xnor(bits, a[g][0], b0.x);          \
-        bits = and_xnor(bits, a[g][1], b0.y);          \
-        bits = and_xnor(bits, a[g][2], b0.z);          \
-        bits = and_xnor(bits, a[g][3], b0.w);          \
-        bits = and_xnor(bits, a[g][4], b1.x);          \
-        bits = and_xnor(bits, a[g][5], b1.y);          \
-        bits = and_xnor(bits, a[g][6], b1.z);          \
-        bits = and_xnor(bits, a[g][7], b1.w);          \
-        bits = and_xnor(bits, a[g][8], b2.x);          \
-        bits = and_xnor(bits, a[g][9], b2.y);          \
-        bits = and_xnor(bits, a[g][10], b2.z);         \
-        bits = and_xnor(bits, a[g][11], b2.w);         \
-        bits = and_xnor(bits, a[g][12], b3.x);         \
-        bits = and_xnor(bits, a[g][13], b3.y);         \
-        c[g] = __popc(bits);                           \
-    }
-                    // first half of this column's chains
-                    PPB_CHAIN(0) PPB_CHAIN(1) PPB_CHAIN(2) PPB_CHAIN(3)
+                    // four AND-chains advance together, plane by plane: a dependent LOP3 is always >= 4
+                    // instructions behind its producer, so one warp alone can keep the ALU pipe full
+                    {
+                        uint32_t x0 = valid, x1 = valid, x2 = valid, x3 = valid;
+#pragma unroll
+                        for (int q = 0; q < kBbits; q++) {
+                            x0 = and_xnor(x0, a[0][q], bw[q]);
+                            x1 = and_xnor(x1, a[1][q], bw[q]);
+                            x2 = and_xnor(x2, a[2][q], bw[q]);
+                            x3 = and_xnor(x3, a[3][q], bw[q]);
+                        }
+                        c[0] = __popc(x0), c[1] = __popc(x1), c[2] = __popc(x2), c[3] = __popc(x3);
+                    }
                     // previous column: warp-sum of its packed counts (inputs were ready an iteration ago)
                     const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
-                    // second half
-                    PPB_CHAIN(4) PPB_CHAIN(5) PPB_CHAIN(6) PPB_CHAIN(7)
-#undef PPB_CHAIN
+                    {
+                        uint32_t x0 = valid, x1 = valid, x2 = valid, x3 = valid;
+#pragma unroll
+                        for (int q = 0; q < kBbits; q++) {
+                            x0 = and_xnor(x0, a[4][q], bw[q]);
+                            x1 = and_xnor(x1, a[5][q], bw[q]);
+                            x2 = and_xnor(x2, a[6][q], bw[q]);
+                            x3 = and_xnor(x3, a[7][q], bw[q]);
+                        }
+                        c[4] = __popc(x0), c[5] = __popc(x1), c[6] = __popc(x2), c[7] = __popc(x3);
+                    }
                     store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
                     // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
                     pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]), pk2 = pack2(c[4], c[5]), pk3 = pack2(c[6], c[7]);
