@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                     const uint32_t *src = p.B + ((int64_t)ks * p.nB_pad + j0) * kSliceWords;
                     for (int jb = 0; jb < n_jb; jb++, it++) {
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_wait_relaxed(&empty[s], ph ^ 1, 100);
                         mbar_arrive_expect_tx(&full[s], kStageBytes);
                         tma_load_1d(stage_base + s * kStageBytes, src + (int64_t)jb * kJB * kSliceWords,
                                     kStageBytes, &full[s]);
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
             const int2 tc = p.tiles[tile];
             const uint32_t b = lt % kCntBufs, ph = (lt / kCntBufs) & 1;
-            mbar_wait(&cfull[b], ph);
+            mbar_wait_relaxed(&cfull[b], ph, 500);
             const uint32_t *cnt = reinterpret_cast<const uint32_t *>(smem + L.off_cnt + b * L.cnt_bytes);
             tile_epilogue(p, cnt, rinfo, (int64_t)tc.x * kTI, (int64_t)tc.y * tj, et, lane);
             __syncwarp();

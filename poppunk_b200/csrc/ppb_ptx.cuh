@@ -38,6 +38,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// Same, for warps that are NOT on the critical path (TMA producer, epilogue): back off between polls so the
+// spin does not take issue slots from the compute warps sharing the scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
+    uint32_t done;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(sleep_ns);
+    }
+}
+
 // ---- TMA: 1-D bulk global -> shared copy, completion on an mbarrier (SASS: UBLKCP) -----------
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
