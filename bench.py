@@ -223,63 +223,93 @@ def run_gpu(args):
     sk = synth.synth_sketches_torch(n, KMERS, SS64, seed=SEED, device=dev)     # identical on every rank
     torch.cuda.synchronize()
     b, e, slice_len = engine.shard_rows(total, world, rank)
-    full = torch.empty((world * slice_len, 2), dtype=torch.float32, device=dev)
-    mine = full[rank * slice_len:(rank + 1) * slice_len]
+    rows_rank = e - b
     ndeg = torch.zeros(1, dtype=torch.int64, device=dev)
-    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-
-    def step(timed=False):
-        packed = engine.pack(sk)
-        if timed:
-            ev_k0.record()
-        engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=mine[:e - b], n_degenerate=ndeg)
-        if timed:
-            ev_k1.record()
-        if world > 1:
-            dist.all_gather_into_tensor(full, mine)
-        return packed
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = L.ppb_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step(timed=True)
-        # the per-launch kernel time needs its own sync-free events: read them after the loop for the last step
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = L.ppb_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    # per-launch duration of the dominant kernel, on the launching stream (separate short loop, same inputs)
+    def timed_loop(step):
+        """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.ppb_launch_count()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, L.ppb_launch_count() - n0
+
+    exchange_desc = "none (single GPU)"
+    nccl_ms = None
+    sampler = None
+    if world == 1:
+        out = torch.empty((total, 2), dtype=torch.float32, device=dev)
+
+        def step():
+            packed = engine.pack(sk)
+            engine.query(packed, None, KMERS, out=out, n_degenerate=ndeg)
+
+        sampler = ClockSampler(local)
+        ms_step, launches = timed_loop(step)
+        clocks = sampler.stop()
+        mine = out
+    else:
+        # (a) NCCL: static row shards + one in-place all_gather_into_tensor per step
+        full = torch.empty((world * slice_len, 2), dtype=torch.float32, device=dev)
+        mine = full[rank * slice_len:(rank + 1) * slice_len]
+
+        def step_nccl():
+            packed = engine.pack(sk)
+            engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=mine[:rows_rank], n_degenerate=ndeg)
+            dist.all_gather_into_tensor(full, mine)
+
+        nccl_ms, _ = timed_loop(step_nccl)
+        del full, mine
+        torch.cuda.empty_cache()
+        # (b) fused: the kernel's epilogue warps store every row into all ranks' buffers (NVSwitch multicast
+        #     when available, else peer stores) — no collective call at all; this is the headline number
+        ex = engine.FusedExchange(total, dev)
+        exchange_desc = ("fused in-kernel exchange: " + ("multimem.st (NVSwitch multicast)" if ex.mc_ptr else
+                         f"{world} coalesced peer stores per row over NVLink") + ", symmetric memory, no all-gather")
+
+        def step():
+            packed = engine.pack(sk)
+            ex.run(packed, None, KMERS, n_degenerate=ndeg)
+
+        if rank == 0:
+            sampler = ClockSampler(local)
+        ms_step, launches = timed_loop(step)
+        clocks = sampler.stop() if sampler else None
+        mine = ex.full[b:e]
+    value = total / (ms_step * 1e-3)
+
+    # per-launch duration of the dominant kernel, on the launching stream (same inputs, local shard only)
     packed = engine.pack(sk)
+    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    scratch = mine[:rows_rank]
     for _ in range(args.steps):
         ev_k0.record()
-        engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=mine[:e - b], n_degenerate=ndeg)
+        engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=scratch, n_degenerate=ndeg)
         ev_k1.record()
         torch.cuda.synchronize()
         kernel_ms.append(ev_k0.elapsed_time(ev_k1))
     ndeg.zero_()
-    engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=mine[:e - b], n_degenerate=ndeg)
+    engine.query(packed, None, KMERS, row_begin=b, row_end=e, out=scratch, n_degenerate=ndeg)
     if world > 1:
         dist.all_reduce(ndeg)
     n_degenerate = int(ndeg.item())
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = total / (ms_step * 1e-3)
     k_ms = float(np.mean(kernel_ms))
-    rows_rank = e - b
+    full = None
 
     # ---- e2e through the host-buffer C-ABI call (pinned host buffers, copies inside the timed region)
     e2e = None
@@ -288,7 +318,9 @@ def run_gpu(args):
         sk_host.copy_(sk)
         out_host = torch.empty((rows_rank, 2), dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
-        del full, mine, packed
+        del packed, scratch
+        if world == 1:
+            del out, mine
         torch.cuda.empty_cache()
         ref_np = sk_host.numpy().view(np.uint64)
         out_np = out_host.numpy()
@@ -311,9 +343,9 @@ def run_gpu(args):
                "api": "ppb_query_host (poppunk_b200.engine.query_host) on pinned host buffers"
                       + ("; each rank copies its own row shard back" if world > 1 else "")}
         checksum = float(out_np[: min(rows_rank, 1 << 20)].sum())
-    except Exception as ex:  # e.g. the box cannot pin a 40 GB result buffer
-        log(f"[bench] e2e leg failed: {ex!r}")
-        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
+    except Exception as err:  # e.g. the box cannot pin a 40 GB result buffer
+        log(f"[bench] e2e leg failed: {err!r}")
+        e2e = {"value": None, "unit": UNIT, "error": repr(err)[:200]}
         checksum = None
         ref_np = sk.cpu().numpy().view(np.uint64)
 
@@ -388,11 +420,14 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"self all-vs-all, N={n}, S=1024 (sketchsize64=16, bbits=14), K=5 (k=13..29 step 4), "
                                f"{total} pairs -> condensed (pairs x 2) float32{note}",
-                   "parallelism": f"{world} rank(s): replicated sketches, static condensed-row shards"
-                                  + (", one NCCL all_gather_into_tensor inside the step" if world > 1 else ""),
+                   "parallelism": f"{world} rank(s): replicated sketches, static condensed-row shards",
+                   "exchange": exchange_desc,
                    "cache": "inputs (0.9 GB) and output (40 GB) are larger than the 126 MB L2; no flush needed",
-                   "step": "pack_kernel + query_kernel (+ all-gather)"},
+                   "step": "pack_kernel + ytab_kernel + query_kernel"},
         "roofline": roofline, "int_pipe": int_pipe, "cpu_baseline": cpu, "e2e": e2e,
+        "nccl_allgather": (None if nccl_ms is None else {
+            "ms_per_step": nccl_ms, "value": total / (nccl_ms * 1e-3), "unit": UNIT,
+            "note": "same step with the exchange done by one NCCL all_gather_into_tensor instead of in-kernel stores"}),
         "gpu_launches": int(launches), "clocks": clocks,
         "n_degenerate": n_degenerate,
     }))

@@ -44,6 +44,7 @@ extern "C" {
 #define PPB_VERSION 100          /* 0.1.0 */
 #define PPB_BBITS 14             /* signature bits per bin (pp-sketchlib constant) */
 #define PPB_MAX_K 32             /* max number of k-mer lengths in one call */
+#define PPB_MAX_PEERS 16         /* max peer output buffers of the fused multi-GPU form */
 #define PPB_MIN_JACCARD_BINS 5   /* J < 5/S ends the regression series (docs/sketching.rst:161-165) */
 
 /* output modes: what one output row holds */
@@ -109,6 +110,21 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref,
                   int32_t out_mode, void *d_out,
                   const ppb_boundary *boundary, int8_t *d_labels,
                   unsigned long long *d_n_degenerate, void *stream);
+
+/* Fused compute + exchange for multi-GPU runs (PPB_OUT_DISTS only).  Same as ppb_query_dev, but every result
+ * row is additionally stored — from inside the kernel's epilogue, over NVLink — into each of the n_peers FULL
+ * result buffers d_peer_out[g] (float32 [total_rows][2] on every GPU, indexed by GLOBAL row; e.g. the
+ * buffer_ptrs of a torch symmetric-memory allocation, this GPU's own buffer included), or, when d_mc_out is not
+ * NULL, once through that NVSwitch multicast address (multimem.st).  After all ranks have run it and passed a
+ * barrier, every GPU holds the whole row-ordered result: no all-gather.  d_out (local shard) may be NULL.    */
+int ppb_query_dev_fused(const uint32_t *d_ref_packed, int64_t n_ref,
+                        const uint32_t *d_qry_packed, int64_t n_qry,
+                        const int32_t *kmers, int32_t K, int32_t sketchsize64,
+                        const float *d_rand_table, int32_t n_clusters,
+                        const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                        int64_t row_begin, int64_t row_end, void *d_out,
+                        void *const *d_peer_out, int32_t n_peers, void *d_mc_out,
+                        unsigned long long *d_n_degenerate, void *stream);
 
 /* Standalone assign_threshold over an existing (n,2) float32 row-major array
  * (src/boundary.cpp:60-80). d_out float32 [n] in {-1,0,+1}.                                  */

@@ -15,7 +15,7 @@ MAX_K = 32
 # every symbol include/ppb.h declares (tests check the .so exports each of them)
 SYMBOLS = [
     "ppb_version", "ppb_last_error", "ppb_device_count", "ppb_square_to_condensed", "ppb_calc_row_idx",
-    "ppb_calc_col_idx", "ppb_num_rows", "ppb_packed_bytes", "ppb_pack_dev", "ppb_query_dev",
+    "ppb_calc_col_idx", "ppb_num_rows", "ppb_packed_bytes", "ppb_pack_dev", "ppb_query_dev", "ppb_query_dev_fused",
     "ppb_assign_threshold_dev", "ppb_query_host", "ppb_assign_threshold_host", "ppb_microbench_dev",
     "ppb_launch_count",
 ]
@@ -62,6 +62,8 @@ def load():
     L.ppb_pack_dev.restype = C.c_int
     L.ppb_query_dev.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
     L.ppb_query_dev.restype = C.c_int
+    L.ppb_query_dev_fused.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, i32, vp, vp, i64, i64, vp, vp, i32, vp, vp, vp]
+    L.ppb_query_dev_fused.restype = C.c_int
     L.ppb_assign_threshold_dev.argtypes = [vp, i64, i32, f32, f32, vp, vp]
     L.ppb_assign_threshold_dev.restype = C.c_int
     L.ppb_query_host.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp,

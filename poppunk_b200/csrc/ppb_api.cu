@@ -163,19 +163,22 @@ int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, 
     return PPB_OK;
 }
 
-int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
-                  const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
-                  int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
-                  int64_t row_begin, int64_t row_end, int32_t out_mode, void *d_out,
-                  const ppb_boundary *boundary, int8_t *d_labels, unsigned long long *d_n_degenerate,
-                  void *stream) {
+static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
+                          const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
+                          int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                          int64_t row_begin, int64_t row_end, int32_t out_mode, void *d_out,
+                          const ppb_boundary *boundary, int8_t *d_labels, unsigned long long *d_n_degenerate,
+                          void *stream, void *const *d_peer_out, int32_t n_peers, void *d_mc_out) {
     const int self = d_qry_packed == nullptr;
     if (!d_ref_packed || !kmers || K < 1 || K > PPB_MAX_K || n_ref < 0 || (!self && n_qry < 0))
         return fail(PPB_ERR_ARG, "ppb_query_dev: bad argument");
     if (sketchsize64 < 1 || sketchsize64 > 1023)
         return fail(PPB_ERR_ARG, "ppb_query_dev: sketchsize64 must be in [1, 1023] (uint16 per-k counts)");
     if (out_mode < PPB_OUT_DISTS || out_mode > PPB_OUT_COUNTS) return fail(PPB_ERR_ARG, "ppb_query_dev: bad out_mode");
-    if (!d_out && !(out_mode == PPB_OUT_DISTS && boundary && d_labels))
+    const bool has_peers = (n_peers > 0 && d_peer_out) || d_mc_out;
+    if (n_peers < 0 || n_peers > PPB_MAX_PEERS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: bad n_peers");
+    if (has_peers && out_mode != PPB_OUT_DISTS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: PPB_OUT_DISTS only");
+    if (!d_out && !has_peers && !(out_mode == PPB_OUT_DISTS && boundary && d_labels))
         return fail(PPB_ERR_ARG, "ppb_query_dev: no output buffer");
     if ((boundary != nullptr) != (d_labels != nullptr))
         return fail(PPB_ERR_ARG, "ppb_query_dev: boundary and d_labels go together");
@@ -212,6 +215,9 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     p.out_mode = out_mode;
     p.out = d_out;
     p.labels = d_labels;
+    p.mc_out = d_mc_out;
+    if (!d_mc_out && d_peer_out)
+        for (int g = 0; g < n_peers; g++) p.peer_out[p.n_peer_out++] = d_peer_out[g];
     p.has_boundary = boundary != nullptr;
     if (boundary) p.bnd = *boundary;
     p.rand_table = d_rand_table;
@@ -296,6 +302,28 @@ int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d
     PPB_CUDA(cudaGetLastError());
     if (d_ytab) PPB_CUDA(cudaFreeAsync(d_ytab, st));
     return PPB_OK;
+}
+
+int ppb_query_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
+                  const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
+                  int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                  int64_t row_begin, int64_t row_end, int32_t out_mode, void *d_out,
+                  const ppb_boundary *boundary, int8_t *d_labels, unsigned long long *d_n_degenerate,
+                  void *stream) {
+    return query_dev_impl(d_ref_packed, n_ref, d_qry_packed, n_qry, kmers, K, sketchsize64, d_rand_table, n_clusters,
+                          d_ref_cluster, d_qry_cluster, row_begin, row_end, out_mode, d_out, boundary, d_labels,
+                          d_n_degenerate, stream, nullptr, 0, nullptr);
+}
+
+int ppb_query_dev_fused(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
+                        const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
+                        int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                        int64_t row_begin, int64_t row_end, void *d_out, void *const *d_peer_out, int32_t n_peers,
+                        void *d_mc_out, unsigned long long *d_n_degenerate, void *stream) {
+    if ((!d_peer_out || n_peers < 1) && !d_mc_out) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: no peer buffers");
+    return query_dev_impl(d_ref_packed, n_ref, d_qry_packed, n_qry, kmers, K, sketchsize64, d_rand_table, n_clusters,
+                          d_ref_cluster, d_qry_cluster, row_begin, row_end, PPB_OUT_DISTS, d_out, nullptr, nullptr,
+                          d_n_degenerate, stream, d_peer_out, n_peers, d_mc_out);
 }
 
 int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, float x_max, float y_max,

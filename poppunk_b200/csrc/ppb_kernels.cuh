@@ -58,7 +58,12 @@ struct QueryParams {
     int64_t n_tiles;
     int64_t row_begin, row_end;
     int32_t out_mode;
-    void *out;
+    void *out;            // row r of the shard is written at index r - row_begin
+    // fused multi-GPU exchange (PPB_OUT_DISTS): every row is ALSO stored into these peer buffers (NVLink-mapped,
+    // indexed by global row), or once through an NVSwitch multicast address — replaces the all-gather
+    void *peer_out[PPB_MAX_PEERS];
+    int32_t n_peer_out;
+    void *mc_out;
     int8_t *labels;
     int32_t has_boundary;
     ppb_boundary bnd;
@@ -214,6 +219,13 @@ __device__ __forceinline__ void store_pair(const QueryParams &p, double sy, doub
         acc = alpha < 0.0 ? (float)(1.0 - exp_nonpos(alpha)) : 0.0f;
     }  // else D3: fewer than two usable k -> (0, 0), counted by the caller
     if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    if (p.mc_out) {  // one store, replicated to every GPU by the NVSwitch (multimem)
+        float2 *dst = reinterpret_cast<float2 *>(p.mc_out) + (row + p.row_begin);
+        asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(core), "f"(acc) : "memory");
+    } else {
+        for (int g = 0; g < p.n_peer_out; g++)  // peer stores over NVLink (write-only, coalesced 256 B per warp row)
+            reinterpret_cast<float2 *>(p.peer_out[g])[row + p.row_begin] = make_float2(core, acc);
+    }
     if (p.has_boundary) {
         // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
         const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
