@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner out of it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 KMERS = np.array([13, 17, 21, 25, 29], dtype=np.int32)   # PopPUNK defaults: k = 13..29 step 4 (__main__.py:77-79)
 SS64 = 16                                                # S = 1024 bins

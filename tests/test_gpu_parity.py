@@ -273,3 +273,19 @@ def test_cfg2_full_size_properties(eng, oracle):
     for b in starts:
         exp, _ = oracle.query(ref, None, KMERS, tab, cl, row_begin=int(b), row_end=int(b) + 4000)
         assert np.abs(host[b:b + 4000] - exp).max() <= TOL
+
+
+# ---------------------------------------------------------------- multi-GPU (needs >= 2 devices; see tests/multigpu_check.py)
+def test_multigpu_paths_match_single_gpu(eng):
+    """Spawns tests/multigpu_check.py under torchrun on 2 GPUs: NCCL all-gather path, fused peer-store exchange and
+    (if the fabric has it) the multimem.st exchange must be byte-identical to the single-GPU result."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "multigpu_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
