@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libppb.so")
+LIB_PATH = os.environ.get("PPB_LIB") or os.path.join(HERE, "libppb.so")   # PPB_LIB: kernel-variant experiments
 
 OUT_DISTS, OUT_JACCARD, OUT_COUNTS = 0, 1, 2
 BBITS = 14

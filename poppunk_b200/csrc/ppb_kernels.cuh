@@ -37,11 +37,24 @@ constexpr int kSliceBytes = kSliceWords * 4;  // 1792
 constexpr int kRowsPerWarp = 8;               // register-stationary genomes per warp
 constexpr int kComputeWarps = 8;
 constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
-constexpr int kJB = 8;                             // column genomes per pipeline stage
-constexpr int kStages = 3;
-constexpr int kStageBytes = kJB * kSliceBytes;     // 14336
+#ifndef PPB_JB
+#define PPB_JB 4
+#endif
+#ifndef PPB_STAGES
+#define PPB_STAGES 6
+#endif
+#ifndef PPB_EPI_WARPS
+#define PPB_EPI_WARPS 2
+#endif
+#ifndef PPB_JJ_UNROLL
+#define PPB_JJ_UNROLL 4
+#endif
+constexpr int kJB = PPB_JB;                        // column genomes per pipeline stage
+constexpr int kStages = PPB_STAGES;
+constexpr int kJJUnroll = PPB_JJ_UNROLL;           // column-loop unroll inside a stage
+constexpr int kStageBytes = kJB * kSliceBytes;     // 7168
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
-constexpr int kEpiWarps = 2;                       // epilogue warps (fit + stores), off the LOP3 critical path
+constexpr int kEpiWarps = PPB_EPI_WARPS;           // epilogue warps (fit + stores), off the LOP3 critical path
 constexpr int kThreads = (kComputeWarps + 1 + kEpiWarps) * 32;  // + 1 TMA producer warp
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
-#pragma unroll
+#pragma unroll kJJUnroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
