@@ -145,6 +145,9 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref,
                    const ppb_boundary *boundary, int8_t *labels,
                    int64_t *n_degenerate, int32_t device_id);
 
+/* Frees the device workspace the host-buffer calls keep between invocations (grow-only, per device). */
+int ppb_release_workspace(void);
+
 int ppb_assign_threshold_host(const float *dists, int64_t n, int32_t slope,
                               float x_max, float y_max, float *out, int32_t device_id);
 

@@ -17,7 +17,7 @@ SYMBOLS = [
     "ppb_version", "ppb_last_error", "ppb_device_count", "ppb_square_to_condensed", "ppb_calc_row_idx",
     "ppb_calc_col_idx", "ppb_num_rows", "ppb_packed_bytes", "ppb_pack_dev", "ppb_query_dev", "ppb_query_dev_fused",
     "ppb_assign_threshold_dev", "ppb_query_host", "ppb_assign_threshold_host", "ppb_microbench_dev",
-    "ppb_launch_count",
+    "ppb_launch_count", "ppb_release_workspace",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
     L.ppb_query_host.restype = C.c_int
     L.ppb_assign_threshold_host.argtypes = [vp, i64, i32, f32, f32, vp, i32]
     L.ppb_assign_threshold_host.restype = C.c_int
+    L.ppb_release_workspace.restype = C.c_int
     L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]
     L.ppb_microbench_dev.restype = C.c_int
     _lib = L

@@ -94,11 +94,15 @@ int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
         PPB_CUDA(cudaMemcpyAsync(tl.d, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
         PPB_CUDA(cudaStreamSynchronize(stream));  // v dies at scope exit
     }
-    if (g_tiles.size() >= 16) {  // tiny LRU-less cache: drop everything when it grows
-        for (auto &kv : g_tiles) cudaFree(kv.second.d);
-        g_tiles.clear();
+    // bounded cache (a chunked host call uses one list per row chunk: ~40 for N=100k); evict oldest first
+    static std::vector<TileKey> order;
+    if (g_tiles.size() >= 256) {
+        cudaFree(g_tiles[order.front()].d);
+        g_tiles.erase(order.front());
+        order.erase(order.begin());
     }
     g_tiles[key] = tl;
+    order.push_back(key);
     *out = tl;
     return PPB_OK;
 }
@@ -379,6 +383,36 @@ struct DevBuf {
         return PPB_OK;
     }
 };
+// Grow-only device workspace reused by successive host-buffer calls on the same device (cudaMalloc/cudaFree of
+// multi-GB buffers per call would otherwise show up in the end-to-end time).  Host calls on one device are
+// serialised by the slot mutex; ppb_release_workspace() returns the memory.
+struct Workspace {
+    std::mutex mu;
+    std::map<std::pair<int, int>, std::pair<void *, size_t>> slots;  // (device, slot) -> (ptr, capacity)
+    int get(int dev, int slot, size_t bytes, void **out) {
+        auto &e = slots[{dev, slot}];
+        if (e.second < bytes || !e.first) {
+            if (e.first) cudaFree(e.first);
+            e.first = nullptr;
+            e.second = 0;
+            if (cudaMalloc(&e.first, std::max<size_t>(bytes, 256)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(PPB_ERR_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+            }
+            e.second = std::max<size_t>(bytes, 256);
+        }
+        *out = e.first;
+        return PPB_OK;
+    }
+    void release() {
+        for (auto &kv : slots)
+            if (kv.second.first) cudaFree(kv.second.first);
+        slots.clear();
+    }
+};
+Workspace g_ws;
+enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_OUT0, WS_OUT1, WS_LAB0, WS_LAB1 };
+
 struct Stream {
     cudaStream_t s = nullptr;
     ~Stream() {
@@ -416,38 +450,42 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     PPB_CUDA(cudaStreamCreateWithFlags(&s_compute.s, cudaStreamNonBlocking));
     PPB_CUDA(cudaStreamCreateWithFlags(&s_copy.s, cudaStreamNonBlocking));
 
+    std::lock_guard<std::mutex> ws_lock(g_ws.mu);  // one host call at a time shares the device workspace
+    auto ws = [&](int slot, size_t bytes, void **ptr) { return g_ws.get(device_id, slot, bytes, ptr); };
+
     const int64_t W = (int64_t)sketchsize64 * PPB_BBITS;
     const size_t ref_bytes = (size_t)n_ref * K * W * 8, qry_bytes = self ? 0 : (size_t)n_qry * K * W * 8;
-    DevBuf d_ref_raw, d_qry_raw, d_ref, d_qry, d_tab, d_rc, d_qc, d_deg;
-    if (int rc = d_ref_raw.alloc(ref_bytes)) return rc;
-    if (int rc = d_ref.alloc(ppb_packed_bytes(n_ref, K, sketchsize64))) return rc;
-    PPB_CUDA(cudaMemcpyAsync(d_ref_raw.p, ref, ref_bytes, cudaMemcpyHostToDevice, s_compute.s));
-    if (int rc = ppb_pack_dev((const uint64_t *)d_ref_raw.p, n_ref, nullptr, n_ref, K, sketchsize64, (uint32_t *)d_ref.p,
+    void *d_ref_raw = nullptr, *d_qry_raw = nullptr, *d_ref = nullptr, *d_qry = nullptr, *d_tab = nullptr,
+         *d_rc = nullptr, *d_qc = nullptr, *d_deg = nullptr;
+    if (int rc = ws(WS_REF_RAW, ref_bytes, &d_ref_raw)) return rc;
+    if (int rc = ws(WS_REF, ppb_packed_bytes(n_ref, K, sketchsize64), &d_ref)) return rc;
+    PPB_CUDA(cudaMemcpyAsync(d_ref_raw, ref, ref_bytes, cudaMemcpyHostToDevice, s_compute.s));
+    if (int rc = ppb_pack_dev((const uint64_t *)d_ref_raw, n_ref, nullptr, n_ref, K, sketchsize64, (uint32_t *)d_ref,
                               s_compute.s))
         return rc;
     if (!self) {
-        if (int rc = d_qry_raw.alloc(qry_bytes)) return rc;
-        if (int rc = d_qry.alloc(ppb_packed_bytes(n_qry, K, sketchsize64))) return rc;
-        PPB_CUDA(cudaMemcpyAsync(d_qry_raw.p, qry, qry_bytes, cudaMemcpyHostToDevice, s_compute.s));
-        if (int rc = ppb_pack_dev((const uint64_t *)d_qry_raw.p, n_qry, nullptr, n_qry, K, sketchsize64,
-                                  (uint32_t *)d_qry.p, s_compute.s))
+        if (int rc = ws(WS_QRY_RAW, qry_bytes, &d_qry_raw)) return rc;
+        if (int rc = ws(WS_QRY, ppb_packed_bytes(n_qry, K, sketchsize64), &d_qry)) return rc;
+        PPB_CUDA(cudaMemcpyAsync(d_qry_raw, qry, qry_bytes, cudaMemcpyHostToDevice, s_compute.s));
+        if (int rc = ppb_pack_dev((const uint64_t *)d_qry_raw, n_qry, nullptr, n_qry, K, sketchsize64,
+                                  (uint32_t *)d_qry, s_compute.s))
             return rc;
     }
     if (rand_table) {
         if (n_clusters < 1 || !ref_cluster || (!self && !qry_cluster))
             return fail(PPB_ERR_ARG, "ppb_query_host: random table without cluster ids");
         const size_t tb = (size_t)n_clusters * n_clusters * K * sizeof(float);
-        if (int rc = d_tab.alloc(tb)) return rc;
-        if (int rc = d_rc.alloc((size_t)n_ref * 2)) return rc;
-        PPB_CUDA(cudaMemcpyAsync(d_tab.p, rand_table, tb, cudaMemcpyHostToDevice, s_compute.s));
-        PPB_CUDA(cudaMemcpyAsync(d_rc.p, ref_cluster, (size_t)n_ref * 2, cudaMemcpyHostToDevice, s_compute.s));
+        if (int rc = ws(WS_TAB, tb, &d_tab)) return rc;
+        if (int rc = ws(WS_RC, (size_t)n_ref * 2, &d_rc)) return rc;
+        PPB_CUDA(cudaMemcpyAsync(d_tab, rand_table, tb, cudaMemcpyHostToDevice, s_compute.s));
+        PPB_CUDA(cudaMemcpyAsync(d_rc, ref_cluster, (size_t)n_ref * 2, cudaMemcpyHostToDevice, s_compute.s));
         if (!self) {
-            if (int rc = d_qc.alloc((size_t)n_qry * 2)) return rc;
-            PPB_CUDA(cudaMemcpyAsync(d_qc.p, qry_cluster, (size_t)n_qry * 2, cudaMemcpyHostToDevice, s_compute.s));
+            if (int rc = ws(WS_QC, (size_t)n_qry * 2, &d_qc)) return rc;
+            PPB_CUDA(cudaMemcpyAsync(d_qc, qry_cluster, (size_t)n_qry * 2, cudaMemcpyHostToDevice, s_compute.s));
         }
     }
-    if (int rc = d_deg.alloc(8)) return rc;
-    PPB_CUDA(cudaMemsetAsync(d_deg.p, 0, 8, s_compute.s));
+    if (int rc = ws(WS_DEG, 8, &d_deg)) return rc;
+    PPB_CUDA(cudaMemsetAsync(d_deg, 0, 8, s_compute.s));
 
     // row chunks, double-buffered: kernel(c) on s_compute overlaps D2H(c-1) on s_copy
     const int rb = out_row_bytes(out_mode, K);
@@ -457,13 +495,13 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     int64_t chunk = std::min<int64_t>(rows, (int64_t)1 << 27);  // 128 Mi rows = 1 GiB of float2 per buffer
     const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
     while (chunk > 1024 && (size_t)(2 * chunk * per_row) > free_b / 2) chunk >>= 1;
-    DevBuf d_out[2], d_lab[2];
+    void *d_out[2] = {nullptr, nullptr}, *d_lab[2] = {nullptr, nullptr};
     Event done_compute[2], done_copy[2];
     for (int b = 0; b < 2; b++) {
         if (out)
-            if (int rc = d_out[b].alloc((size_t)chunk * rb)) return rc;
+            if (int rc = ws(WS_OUT0 + b, (size_t)chunk * rb, &d_out[b])) return rc;
         if (labels)
-            if (int rc = d_lab[b].alloc((size_t)chunk)) return rc;
+            if (int rc = ws(WS_LAB0 + b, (size_t)chunk, &d_lab[b])) return rc;
         PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
         PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
     }
@@ -472,27 +510,33 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
         const int b = (int)(c & 1);
         const int64_t r1 = std::min(row_end, r0 + chunk);
         if (c >= 2) PPB_CUDA(cudaStreamWaitEvent(s_compute.s, done_copy[b].e, 0));  // buffer b drained
-        if (int rc = ppb_query_dev((const uint32_t *)d_ref.p, n_ref, self ? nullptr : (const uint32_t *)d_qry.p, n_qry,
-                                   kmers, K, sketchsize64, (const float *)d_tab.p, n_clusters,
-                                   (const uint16_t *)d_rc.p, (const uint16_t *)d_qc.p, r0, r1, out_mode,
-                                   out ? d_out[b].p : nullptr, boundary, labels ? (int8_t *)d_lab[b].p : nullptr,
-                                   (unsigned long long *)d_deg.p, s_compute.s))
+        if (int rc = ppb_query_dev((const uint32_t *)d_ref, n_ref, self ? nullptr : (const uint32_t *)d_qry, n_qry,
+                                   kmers, K, sketchsize64, (const float *)d_tab, n_clusters,
+                                   (const uint16_t *)d_rc, (const uint16_t *)d_qc, r0, r1, out_mode,
+                                   out ? d_out[b] : nullptr, boundary, labels ? (int8_t *)d_lab[b] : nullptr,
+                                   (unsigned long long *)d_deg, s_compute.s))
             return rc;
         PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
         PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
         if (out)
-            PPB_CUDA(cudaMemcpyAsync((char *)out + (size_t)(r0 - row_begin) * rb, d_out[b].p, (size_t)(r1 - r0) * rb,
+            PPB_CUDA(cudaMemcpyAsync((char *)out + (size_t)(r0 - row_begin) * rb, d_out[b], (size_t)(r1 - r0) * rb,
                                      cudaMemcpyDeviceToHost, s_copy.s));
         if (labels)
-            PPB_CUDA(cudaMemcpyAsync(labels + (r0 - row_begin), d_lab[b].p, (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
+            PPB_CUDA(cudaMemcpyAsync(labels + (r0 - row_begin), d_lab[b], (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
                                      s_copy.s));
         PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
     }
     unsigned long long deg = 0;
-    PPB_CUDA(cudaMemcpyAsync(&deg, d_deg.p, 8, cudaMemcpyDeviceToHost, s_compute.s));
+    PPB_CUDA(cudaMemcpyAsync(&deg, d_deg, 8, cudaMemcpyDeviceToHost, s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_copy.s));
     if (n_degenerate) *n_degenerate = (int64_t)deg;
+    return PPB_OK;
+}
+
+int ppb_release_workspace(void) {
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    g_ws.release();
     return PPB_OK;
 }
 
