@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -51,15 +52,19 @@ inline int64_t col_idx(int64_t k, int64_t i, int64_t n) {
 // Tiles are (kTI rows) x (tj columns).  Order: bands of kBand row-tiles; inside a band the column tile is
 // the slow index, so the CTAs running at any moment share a handful of column tiles (L2 hits) and the
 // band's row genomes stay L2-resident while the columns stream past once per band.
-constexpr int kBand = 64;
+// Band height is chosen per call so that a band's row genomes are ~36 MB (4096 genomes at S=1024, K=5):
+// measured DRAM traffic is flat between 18 and 73 MB bands (profiles/), so the smaller footprint is used.
+constexpr size_t kBandBytes = (size_t)36 << 20;
 
 struct TileKey {
     int dev;
     int64_t nA, nB;
     int self, tj;
     int64_t i_lo, i_hi;
+    int band;  // row tiles per band
     bool operator<(const TileKey &o) const {
-        return std::tie(dev, nA, nB, self, tj, i_lo, i_hi) < std::tie(o.dev, o.nA, o.nB, o.self, o.tj, o.i_lo, o.i_hi);
+        return std::tie(dev, nA, nB, self, tj, i_lo, i_hi, band) <
+               std::tie(o.dev, o.nA, o.nB, o.self, o.tj, o.i_lo, o.i_hi, o.band);
     }
 };
 struct TileList {
@@ -79,6 +84,7 @@ int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
     std::vector<int2> v;
     const int64_t nTi = (key.nA + ppb::kTI - 1) / ppb::kTI, nTj = (key.nB + key.tj - 1) / key.tj;
     const int64_t it_lo = key.i_lo / ppb::kTI, it_hi = key.i_hi / ppb::kTI;
+    const int64_t kBand = std::max(1, key.band);
     for (int64_t b0 = it_lo / kBand * kBand; b0 <= it_hi && b0 < nTi; b0 += kBand) {
         const int64_t b1 = std::min<int64_t>({b0 + kBand, nTi, it_hi + 1});
         for (int64_t jt = 0; jt < nTj; jt++)
@@ -257,14 +263,18 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
     p.tj = tj;
 
-    TileKey key{dev, p.nA, p.nB, self, tj, 0, 0};
-    if (self) {
-        key.i_lo = row_idx(row_begin, n_ref);
-        key.i_hi = row_idx(row_end - 1, n_ref);
-    } else {
-        key.i_lo = row_begin / n_ref;
-        key.i_hi = (row_end - 1) / n_ref;
-    }
+    const size_t genome_bytes = (size_t)p.KS * ppb::kSliceBytes;
+    int band = (int)std::min<size_t>(4096, std::max<size_t>(2, kBandBytes / (genome_bytes * ppb::kTI)));
+    if (const char *e = std::getenv("PPB_BAND_TILES")) band = std::max(1, atoi(e));  // tuning experiments
+    // L2 eviction-priority knobs, all OFF by default: measured on B200 at N=100k (profiles/), streaming stores,
+    // evict_last row-genome loads (with a persisting set-aside) and evict_first column TMA each INCREASED the
+    // DRAM read traffic (50 -> 57..208 GB) and changed the kernel time by < 2 %.  Kept as environment knobs.
+    p.stream_stores = 0;
+    p.a_policy = 0;
+    p.b_policy = 0;
+    if (const char *e = std::getenv("PPB_STREAM_STORES")) p.stream_stores = atoi(e);
+    if (const char *e = std::getenv("PPB_A_POLICY")) p.a_policy = atoi(e);
+    if (const char *e = std::getenv("PPB_B_POLICY")) p.b_policy = atoi(e);
     TileList tl;
     if (int rc = get_tiles(key, st, &tl)) return rc;
     if (tl.n == 0) return PPB_OK;

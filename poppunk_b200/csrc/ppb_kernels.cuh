@@ -77,6 +77,8 @@ struct QueryParams {
     void *peer_out[PPB_MAX_PEERS];
     int32_t n_peer_out;
     void *mc_out;
+    int32_t stream_stores;  // 1: outputs are written evict-first (st.global.cs)
+    int32_t a_policy, b_policy;  // L2 eviction priority of row-genome loads / column-genome TMA (0 normal, 1 last, 2 first)
     int8_t *labels;
     int32_t has_boundary;
     ppb_boundary bnd;
@@ -231,7 +233,13 @@ __device__ __forceinline__ void store_pair(const QueryParams &p, double sy, doub
         core = beta < 0.0 ? (float)(1.0 - exp_nonpos(beta)) : 0.0f;
         acc = alpha < 0.0 ? (float)(1.0 - exp_nonpos(alpha)) : 0.0f;
     }  // else D3: fewer than two usable k -> (0, 0), counted by the caller
-    if (p.out) reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    // streaming store (evict-first): 8 B/pair of output must not push the sketch tiles out of L2
+    if (p.out) {
+        if (p.stream_stores)
+            __stcs(reinterpret_cast<float2 *>(p.out) + row, make_float2(core, acc));
+        else
+            reinterpret_cast<float2 *>(p.out)[row] = make_float2(core, acc);
+    }
     if (p.mc_out) {  // one store, replicated to every GPU by the NVSwitch (multimem)
         float2 *dst = reinterpret_cast<float2 *>(p.mc_out) + (row + p.row_begin);
         asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(core), "f"(acc) : "memory");
@@ -242,7 +250,8 @@ __device__ __forceinline__ void store_pair(const QueryParams &p, double sy, doub
     if (p.has_boundary) {
         // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
         const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
-        p.labels[row] = (int8_t)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope));
+        __stcs(reinterpret_cast<signed char *>(p.labels) + row,
+               (signed char)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope)));
     }
 }
 
@@ -445,6 +454,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     if (warp == kComputeWarps) {
         // ===== TMA producer: streams column-genome slices of every (tile, k, slice) into the ring =====
         if (lane == 0) {
+            const uint64_t pol_b = l2_policy(p.b_policy);
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const int2 tc = p.tiles[tile];
@@ -455,8 +465,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                         mbar_wait_relaxed(&empty[s], ph ^ 1, 100);
                         mbar_arrive_expect_tx(&full[s], kStageBytes);
-                        tma_load_1d(stage_base + s * kStageBytes, src + (int64_t)jb * kJB * kSliceWords,
-                                    kStageBytes, &full[s]);
+                        tma_load_1d_hint(stage_base + s * kStageBytes, src + (int64_t)jb * kJB * kSliceWords,
+                                         kStageBytes, &full[s], pol_b);
                     }
                 }
             }
@@ -486,6 +496,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     // Software pipeline over columns: while the LOP3 stream of column c runs, the packed partial counts of
     // column c-1 go through REDUX and are stored at the end — no POPC/REDUX latency is ever waited for.
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
+    const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
         const int2 tc = p.tiles[tile];
@@ -509,8 +520,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 #pragma unroll
                 for (int g = 0; g < kRowsPerWarp; g++) {
                     const uint4 *q4 = reinterpret_cast<const uint4 *>(ap + g * kSliceWords);
-                    const uint4 v0 = __ldg(q4 + lane), v1 = __ldg(q4 + 32 + lane), v2 = __ldg(q4 + 64 + lane);
-                    const uint2 v3 = __ldg(reinterpret_cast<const uint2 *>(ap + g * kSliceWords + 384) + lane);
+                    const uint4 v0 = ldg128_hint(q4 + lane, pol_a), v1 = ldg128_hint(q4 + 32 + lane, pol_a),
+                                v2 = ldg128_hint(q4 + 64 + lane, pol_a);
+                    const uint2 v3 = ldg64_hint(reinterpret_cast<const uint2 *>(ap + g * kSliceWords + 384) + lane, pol_a);
                     a[g][0] = v0.x, a[g][1] = v0.y, a[g][2] = v0.z, a[g][3] = v0.w;
                     a[g][4] = v1.x, a[g][5] = v1.y, a[g][6] = v1.z, a[g][7] = v1.w;
                     a[g][8] = v2.x, a[g][9] = v2.y, a[g][10] = v2.z, a[g][11] = v2.w;

@@ -61,6 +61,40 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
+// TMA bulk copy with an L2 eviction-priority policy (createpolicy)
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ---- L2 eviction-priority policies ------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict_last (keep), 2 evict_first (stream)
+    uint64_t pol;
+    if (kind == 1)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2)
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg128_hint(const void *ptr, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg64_hint(const void *ptr, uint64_t policy) {
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(policy));
+    return v;
+}
+
 // ---- named barrier among a subset of the CTA's warps -----------------------------------------
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
