@@ -275,6 +275,15 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (const char *e = std::getenv("PPB_STREAM_STORES")) p.stream_stores = atoi(e);
     if (const char *e = std::getenv("PPB_A_POLICY")) p.a_policy = atoi(e);
     if (const char *e = std::getenv("PPB_B_POLICY")) p.b_policy = atoi(e);
+
+    TileKey key{dev, p.nA, p.nB, self, tj, 0, 0, band};
+    if (self) {
+        key.i_lo = row_idx(row_begin, n_ref);
+        key.i_hi = row_idx(row_end - 1, n_ref);
+    } else {
+        key.i_lo = row_begin / n_ref;
+        key.i_hi = (row_end - 1) / n_ref;
+    }
     TileList tl;
     if (int rc = get_tiles(key, st, &tl)) return rc;
     if (tl.n == 0) return PPB_OK;
