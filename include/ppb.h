@@ -131,6 +131,52 @@ int ppb_query_dev_fused(const uint32_t *d_ref_packed, int64_t n_ref,
 int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope,
                              float x_max, float y_max, float *d_out, void *stream);
 
+/* ---------------- "next" rows: consumers of the path's output ----------------------
+ *
+ * N1 — edge lists after the threshold.
+ * ppb_query_edges_dev: the distance kernel with the boundary test fused AND the within-boundary pairs appended,
+ *   as GLOBAL row indices, to d_edge_rows (unordered, warp-aggregated atomics; *d_edge_count may exceed
+ *   capacity — then only `capacity` rows were stored).  include_boundary = 0: line_dist < 0 (what
+ *   generate_tuples does with assign_threshold labels == -1, network.py:1180-1184); 1: line_dist <= 0 (what
+ *   edge_iterate does, src/boundary.cpp:86-87).  d_out / d_labels are optional (NULL = not written).
+ * ppb_rows_to_pairs_dev: rows -> (i, j) sample pairs with generate_tuples' conventions
+ *   (src/boundary.cpp:97-123: self -> calc_row_idx/calc_col_idx + int_offset; non-self -> i = row % num_ref +
+ *   int_offset, j = row / num_ref + num_ref + int_offset; swapped so that i <= j).
+ * ppb_edges_from_dists_dev / ppb_edges_from_labels_dev: ORDERED (ascending row, like the reference loops)
+ *   compaction of an existing (n,2) distance array (edge_iterate, src/boundary.cpp:82-95) or label array
+ *   (generate_tuples; label_dtype 0 = int8, 1 = int32, 2 = float32).  d_scratch: ppb_edges_scratch_bytes(n_rows).
+ *   *d_count receives the number of edges found (pairs beyond `capacity` are not written).                  */
+int ppb_query_edges_dev(const uint32_t *d_ref_packed, int64_t n_ref,
+                        const uint32_t *d_qry_packed, int64_t n_qry,
+                        const int32_t *kmers, int32_t K, int32_t sketchsize64,
+                        const float *d_rand_table, int32_t n_clusters,
+                        const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                        int64_t row_begin, int64_t row_end,
+                        const ppb_boundary *boundary, int32_t include_boundary,
+                        int64_t *d_edge_rows, int64_t capacity, unsigned long long *d_edge_count,
+                        void *d_out, int8_t *d_labels,
+                        unsigned long long *d_n_degenerate, void *stream);
+int ppb_rows_to_pairs_dev(const int64_t *d_rows, int64_t n, int32_t self, int64_t n_samples_or_num_ref,
+                          int64_t int_offset, int64_t *d_i, int64_t *d_j, void *stream);
+size_t ppb_edges_scratch_bytes(int64_t n_rows);
+int ppb_edges_from_dists_dev(const float *d_dists, int64_t n_rows, int64_t n_samples, int32_t slope,
+                             float x_max, float y_max, int64_t *d_i, int64_t *d_j, int64_t capacity,
+                             int64_t *d_count, void *d_scratch, void *stream);
+int ppb_edges_from_labels_dev(const void *d_labels, int32_t label_dtype, int64_t n_rows, int32_t within_label,
+                              int32_t self, int64_t n_samples_or_num_ref, int64_t int_offset,
+                              int64_t *d_i, int64_t *d_j, int64_t capacity, int64_t *d_count,
+                              void *d_scratch, void *stream);
+
+/* N2 — long <-> square reshapes (pp_sketchlib.longToSquare / squareToLong / longToSquareMulti; call sites
+ * PopPUNK/utils.py:393-405, network.py:2133-2134, models.py:1217,1357, mandrake.py:165).  float32; the
+ * condensed / rectangular vectors are read with an element stride so a column of the (n_pairs,2) distance
+ * array can be passed in place (stride 2).  Squares are row-major n x n, symmetric, zero diagonal.          */
+int ppb_long_to_square_dev(const float *d_vec, int64_t stride, int64_t n, float *d_square, void *stream);
+int ppb_square_to_long_dev(const float *d_square, int64_t n, float *d_vec, void *stream);
+int ppb_long_to_square_multi_dev(const float *d_rr, int64_t stride_rr, const float *d_qr, int64_t stride_qr,
+                                 const float *d_qq, int64_t stride_qq, int64_t n_ref, int64_t n_qry,
+                                 float *d_square, void *stream);
+
 /* ---------------- host-buffer entry points (what a pybind/ctypes shim of PopPUNK calls) --
  * Same semantics as above with HOST pointers: the library stages host->device copies,
  * packs, runs the kernels in row chunks and copies results back, overlapping copy and

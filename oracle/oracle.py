@@ -63,6 +63,13 @@ def lib(native: bool = False):
     L.ppo_num_rows.argtypes = [i64, i64, C.c_int]
     L.ppo_num_rows.restype = i64
     L.ppo_max_threads.restype = C.c_int
+    L.ppo_edge_iterate.argtypes = [vp, i64, i32, C.c_float, C.c_float, vp, vp]
+    L.ppo_edge_iterate.restype = i64
+    L.ppo_generate_tuples.argtypes = [vp, i64, i32, i32, i64, i64, vp, vp]
+    L.ppo_generate_tuples.restype = i64
+    L.ppo_long_to_square.argtypes = [vp, i64, i64, vp]
+    L.ppo_square_to_long.argtypes = [vp, i64, vp]
+    L.ppo_long_to_square_multi.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, vp]
     L.ppo_regress_rows.argtypes = [vp, i64, vp, i32, C.c_double, vp]
     L.ppo_regress_rows.restype = i64
     if not native:
@@ -158,6 +165,44 @@ def regress_rows(jac, kmers, S):
     out = np.empty((jac.shape[0], 2), dtype=np.float32)
     deg = lib().ppo_regress_rows(_ptr(jac), jac.shape[0], _ptr(kmers), jac.shape[1], float(S), _ptr(out))
     return out, int(deg)
+
+
+def edge_iterate(dists, slope, x_max, y_max):
+    """src/boundary.cpp:82-95: (i, j) int64 arrays of the rows with line_dist <= 0, in row order."""
+    d = np.ascontiguousarray(dists, dtype=np.float32)
+    oi, oj = np.empty(d.shape[0], dtype=np.int64), np.empty(d.shape[0], dtype=np.int64)
+    n = lib().ppo_edge_iterate(_ptr(d), d.shape[0], slope, x_max, y_max, _ptr(oi), _ptr(oj))
+    return oi[:n], oj[:n]
+
+
+def generate_tuples(assignments, within_label, self=True, num_ref=0, int_offset=0):
+    """src/boundary.cpp:97-123."""
+    a = np.ascontiguousarray(assignments, dtype=np.int32)
+    oi, oj = np.empty(a.shape[0], dtype=np.int64), np.empty(a.shape[0], dtype=np.int64)
+    n = lib().ppo_generate_tuples(_ptr(a), a.shape[0], within_label, int(self), max(num_ref, 1), int_offset, _ptr(oi), _ptr(oj))
+    return oi[:n], oj[:n]
+
+
+def long_to_square(vec, n):
+    v = np.ascontiguousarray(vec, dtype=np.float32).reshape(-1)
+    sq = np.empty((n, n), dtype=np.float32)
+    lib().ppo_long_to_square(_ptr(v), 1, n, _ptr(sq))
+    return sq
+
+
+def square_to_long(sq):
+    sq = np.ascontiguousarray(sq, dtype=np.float32)
+    n = sq.shape[0]
+    v = np.empty(n * (n - 1) // 2, dtype=np.float32)
+    lib().ppo_square_to_long(_ptr(sq), n, _ptr(v))
+    return v
+
+
+def long_to_square_multi(rr, qr, qq, R, Q):
+    rr, qr, qq = (np.ascontiguousarray(x, dtype=np.float32).reshape(-1) for x in (rr, qr, qq))
+    sq = np.empty((R + Q, R + Q), dtype=np.float32)
+    lib().ppo_long_to_square_multi(_ptr(rr), 1, _ptr(qr), 1, _ptr(qq), 1, R, Q, _ptr(sq))
+    return sq
 
 
 def square_to_condensed(i, j, n):

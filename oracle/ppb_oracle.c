@@ -316,3 +316,88 @@ int ppo_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" rows — restated from src/boundary.cpp, which IS in the reference tree.
+ * ---------------------------------------------------------------------------------------- */
+
+/* N1: src/boundary.cpp:82-95 edge_iterate — rows with line_dist <= 0, in row order, as (i, j). Returns count. */
+int64_t ppo_edge_iterate(const float *dists, int64_t n_rows, int32_t slope, float x_max, float y_max,
+                         int64_t *out_i, int64_t *out_j) {
+    const int64_t n_samples = (int64_t)(0.5 * (1 + sqrt(1 + 8.0 * (double)n_rows))); /* rows_to_samples :18-20 */
+    int64_t cnt = 0;
+    for (int64_t row = 0; row < n_rows; row++) {
+        if (ppo_line_dist(dists[2 * row], dists[2 * row + 1], x_max, y_max, slope) <= 0) {
+            const int64_t i = ppo_calc_row_idx(row, n_samples);
+            out_i[cnt] = i;
+            out_j[cnt] = ppo_calc_col_idx(row, i, n_samples);
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
+/* N1: src/boundary.cpp:97-123 generate_tuples. Returns count. */
+int64_t ppo_generate_tuples(const int32_t *assignments, int64_t n_rows, int32_t within_label, int32_t self,
+                            int64_t num_ref, int64_t int_offset, int64_t *out_i, int64_t *out_j) {
+    const int64_t n_samples = (int64_t)(0.5 * (1 + sqrt(1 + 8.0 * (double)n_rows)));
+    int64_t cnt = 0;
+    for (int64_t row = 0; row < n_rows; row++) {
+        if (assignments[row] == within_label) {
+            int64_t i, j;
+            if (self) {
+                i = ppo_calc_row_idx(row, n_samples);
+                j = ppo_calc_col_idx(row, i, n_samples) + int_offset;
+                i = i + int_offset;
+            } else {
+                i = row % num_ref + int_offset;
+                j = row / num_ref + num_ref + int_offset;
+            }
+            if (i > j) {
+                int64_t t = i;
+                i = j;
+                j = t;
+            }
+            out_i[cnt] = i;
+            out_j[cnt] = j;
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
+/* N2: pp_sketchlib.longToSquare / squareToLong / longToSquareMulti [UPSTREAM-RECALL for the bodies; semantics
+ * from the call sites PopPUNK/utils.py:393-405 (square of N = R (+ Q) samples from the condensed ref-ref vector,
+ * the query-major query-ref rectangle and the condensed query-query vector), network.py:2133-2134]. */
+void ppo_long_to_square(const float *vec, int64_t stride, int64_t n, float *sq) {
+    for (int64_t r = 0; r < n; r++) {
+        sq[r * n + r] = 0.0f;
+        for (int64_t c = r + 1; c < n; c++) {
+            const float v = vec[ppo_square_to_condensed(r, c, n) * stride];
+            sq[r * n + c] = v;
+            sq[c * n + r] = v;
+        }
+    }
+}
+void ppo_square_to_long(const float *sq, int64_t n, float *vec) {
+    for (int64_t r = 0; r < n; r++)
+        for (int64_t c = r + 1; c < n; c++) vec[ppo_square_to_condensed(r, c, n)] = sq[r * n + c];
+}
+void ppo_long_to_square_multi(const float *rr, int64_t s_rr, const float *qr, int64_t s_qr, const float *qq,
+                              int64_t s_qq, int64_t R, int64_t Q, float *sq) {
+    const int64_t n = R + Q;
+    for (int64_t r = 0; r < n; r++) {
+        sq[r * n + r] = 0.0f;
+        for (int64_t c = r + 1; c < n; c++) {
+            float v;
+            if (c < R)
+                v = rr[ppo_square_to_condensed(r, c, R) * s_rr];
+            else if (r >= R)
+                v = qq[ppo_square_to_condensed(r - R, c - R, Q) * s_qq];
+            else
+                v = qr[((c - R) * R + r) * s_qr];
+            sq[r * n + c] = v;
+            sq[c * n + r] = v;
+        }
+    }
+}

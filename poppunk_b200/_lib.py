@@ -17,7 +17,9 @@ SYMBOLS = [
     "ppb_version", "ppb_last_error", "ppb_device_count", "ppb_square_to_condensed", "ppb_calc_row_idx",
     "ppb_calc_col_idx", "ppb_num_rows", "ppb_packed_bytes", "ppb_pack_dev", "ppb_query_dev", "ppb_query_dev_fused",
     "ppb_assign_threshold_dev", "ppb_query_host", "ppb_assign_threshold_host", "ppb_microbench_dev",
-    "ppb_launch_count", "ppb_release_workspace",
+    "ppb_launch_count", "ppb_release_workspace", "ppb_query_edges_dev", "ppb_rows_to_pairs_dev",
+    "ppb_edges_scratch_bytes", "ppb_edges_from_dists_dev", "ppb_edges_from_labels_dev", "ppb_long_to_square_dev",
+    "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev",
 ]
 
 
@@ -72,6 +74,23 @@ def load():
     L.ppb_assign_threshold_host.argtypes = [vp, i64, i32, f32, f32, vp, i32]
     L.ppb_assign_threshold_host.restype = C.c_int
     L.ppb_release_workspace.restype = C.c_int
+    L.ppb_query_edges_dev.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, i32, vp, vp, i64, i64, vp, i32, vp, i64, vp,
+                                      vp, vp, vp, vp]
+    L.ppb_query_edges_dev.restype = C.c_int
+    L.ppb_rows_to_pairs_dev.argtypes = [vp, i64, i32, i64, i64, vp, vp, vp]
+    L.ppb_rows_to_pairs_dev.restype = C.c_int
+    L.ppb_edges_scratch_bytes.argtypes = [i64]
+    L.ppb_edges_scratch_bytes.restype = C.c_size_t
+    L.ppb_edges_from_dists_dev.argtypes = [vp, i64, i64, i32, f32, f32, vp, vp, i64, vp, vp, vp]
+    L.ppb_edges_from_dists_dev.restype = C.c_int
+    L.ppb_edges_from_labels_dev.argtypes = [vp, i32, i64, i32, i32, i64, i64, vp, vp, i64, vp, vp, vp]
+    L.ppb_edges_from_labels_dev.restype = C.c_int
+    L.ppb_long_to_square_dev.argtypes = [vp, i64, i64, vp, vp]
+    L.ppb_long_to_square_dev.restype = C.c_int
+    L.ppb_square_to_long_dev.argtypes = [vp, i64, vp, vp]
+    L.ppb_square_to_long_dev.restype = C.c_int
+    L.ppb_long_to_square_multi_dev.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, vp, vp]
+    L.ppb_long_to_square_multi_dev.restype = C.c_int
     L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]
     L.ppb_microbench_dev.restype = C.c_int
     _lib = L

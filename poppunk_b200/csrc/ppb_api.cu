@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ppb_kernels.cuh"
+#include "ppb_next.cuh"
 
 namespace {
 
@@ -178,7 +179,9 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
                           int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
                           int64_t row_begin, int64_t row_end, int32_t out_mode, void *d_out,
                           const ppb_boundary *boundary, int8_t *d_labels, unsigned long long *d_n_degenerate,
-                          void *stream, void *const *d_peer_out, int32_t n_peers, void *d_mc_out) {
+                          void *stream, void *const *d_peer_out, int32_t n_peers, void *d_mc_out,
+                          int32_t edge_mode = 0, int64_t *d_edge_rows = nullptr, int64_t edge_cap = 0,
+                          unsigned long long *d_edge_count = nullptr) {
     const int self = d_qry_packed == nullptr;
     if (!d_ref_packed || !kmers || K < 1 || K > PPB_MAX_K || n_ref < 0 || (!self && n_qry < 0))
         return fail(PPB_ERR_ARG, "ppb_query_dev: bad argument");
@@ -188,10 +191,13 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     const bool has_peers = (n_peers > 0 && d_peer_out) || d_mc_out;
     if (n_peers < 0 || n_peers > PPB_MAX_PEERS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: bad n_peers");
     if (has_peers && out_mode != PPB_OUT_DISTS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: PPB_OUT_DISTS only");
-    if (!d_out && !has_peers && !(out_mode == PPB_OUT_DISTS && boundary && d_labels))
+    const bool has_edges = edge_mode != 0 && d_edge_rows && d_edge_count && boundary;
+    if (edge_mode != 0 && !has_edges) return fail(PPB_ERR_ARG, "ppb_query_edges_dev: edge buffers and a boundary are required");
+    if (!d_out && !has_peers && !has_edges && !(out_mode == PPB_OUT_DISTS && boundary && d_labels))
         return fail(PPB_ERR_ARG, "ppb_query_dev: no output buffer");
-    if ((boundary != nullptr) != (d_labels != nullptr))
+    if (!has_edges && (boundary != nullptr) != (d_labels != nullptr))
         return fail(PPB_ERR_ARG, "ppb_query_dev: boundary and d_labels go together");
+    if (d_labels && !boundary) return fail(PPB_ERR_ARG, "ppb_query_dev: labels need a boundary");
     if (boundary && out_mode != PPB_OUT_DISTS) return fail(PPB_ERR_ARG, "ppb_query_dev: labels need PPB_OUT_DISTS");
     if (boundary && (boundary->slope < 0 || boundary->slope > 2)) return fail(PPB_ERR_ARG, "ppb_query_dev: bad slope");
     if (d_rand_table && (n_clusters < 1 || !d_ref_cluster || (!self && !d_qry_cluster)))
@@ -226,6 +232,10 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     p.out = d_out;
     p.labels = d_labels;
     p.mc_out = d_mc_out;
+    p.edge_mode = has_edges ? edge_mode : 0;
+    p.edge_rows = (long long *)d_edge_rows;
+    p.edge_cap = edge_cap;
+    p.edge_count = d_edge_count;
     if (!d_mc_out && d_peer_out)
         for (int g = 0; g < n_peers; g++) p.peer_out[p.n_peer_out++] = d_peer_out[g];
     p.has_boundary = boundary != nullptr;
@@ -347,6 +357,125 @@ int ppb_query_dev_fused(const uint32_t *d_ref_packed, int64_t n_ref, const uint3
     return query_dev_impl(d_ref_packed, n_ref, d_qry_packed, n_qry, kmers, K, sketchsize64, d_rand_table, n_clusters,
                           d_ref_cluster, d_qry_cluster, row_begin, row_end, PPB_OUT_DISTS, d_out, nullptr, nullptr,
                           d_n_degenerate, stream, d_peer_out, n_peers, d_mc_out);
+}
+
+int ppb_query_edges_dev(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
+                        const int32_t *kmers, int32_t K, int32_t sketchsize64, const float *d_rand_table,
+                        int32_t n_clusters, const uint16_t *d_ref_cluster, const uint16_t *d_qry_cluster,
+                        int64_t row_begin, int64_t row_end, const ppb_boundary *boundary, int32_t include_boundary,
+                        int64_t *d_edge_rows, int64_t capacity, unsigned long long *d_edge_count, void *d_out,
+                        int8_t *d_labels, unsigned long long *d_n_degenerate, void *stream) {
+    if (!boundary || !d_edge_rows || !d_edge_count || capacity < 0)
+        return fail(PPB_ERR_ARG, "ppb_query_edges_dev: bad argument");
+    return query_dev_impl(d_ref_packed, n_ref, d_qry_packed, n_qry, kmers, K, sketchsize64, d_rand_table, n_clusters,
+                          d_ref_cluster, d_qry_cluster, row_begin, row_end, PPB_OUT_DISTS, d_out, boundary, d_labels,
+                          d_n_degenerate, stream, nullptr, 0, nullptr, include_boundary ? 2 : 1, d_edge_rows, capacity,
+                          d_edge_count);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N1 / N2 entry points
+// ---------------------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+inline unsigned grid_for(int64_t n, int threads, int cap) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, cap));
+}
+template <typename Pred>
+int run_select(Pred pred, int64_t n_rows, ppb::PairMap map, int64_t *d_i, int64_t *d_j, int64_t capacity,
+               int64_t *d_count, void *d_scratch, cudaStream_t st) {
+    if (!d_count || !d_scratch || capacity < 0 || (capacity > 0 && (!d_i || !d_j)))
+        return fail(PPB_ERR_ARG, "edge compaction: bad argument");
+    if (n_rows == 0) {
+        PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+        return PPB_OK;
+    }
+    const int64_t blocks = (n_rows + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+    if (blocks > 0x7fffffff) return fail(PPB_ERR_ARG, "edge compaction: too many rows for one call");
+    int64_t *block_off = (int64_t *)d_scratch;
+    ppb::select_kernel<Pred><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(pred, n_rows, map, 0, block_off, capacity, d_i, d_j);
+    ppb::scan_kernel<<<1, 1024, 0, st>>>(block_off, blocks, d_count);
+    ppb::select_kernel<Pred><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(pred, n_rows, map, 1, block_off, capacity, d_i, d_j);
+    g_launches += 3;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+size_t ppb_edges_scratch_bytes(int64_t n_rows) {
+    return (size_t)((std::max<int64_t>(n_rows, 1) + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows) * sizeof(int64_t);
+}
+
+int ppb_rows_to_pairs_dev(const int64_t *d_rows, int64_t n, int32_t self, int64_t n_samples_or_num_ref,
+                          int64_t int_offset, int64_t *d_i, int64_t *d_j, void *stream) {
+    if (n < 0 || (n > 0 && (!d_rows || !d_i || !d_j)) || n_samples_or_num_ref < 1)
+        return fail(PPB_ERR_ARG, "ppb_rows_to_pairs_dev: bad argument");
+    if (n == 0) return PPB_OK;
+    ppb::rows_to_pairs_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        d_rows, n, ppb::PairMap{self, n_samples_or_num_ref, int_offset}, d_i, d_j);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_edges_from_dists_dev(const float *d_dists, int64_t n_rows, int64_t n_samples, int32_t slope, float x_max,
+                             float y_max, int64_t *d_i, int64_t *d_j, int64_t capacity, int64_t *d_count,
+                             void *d_scratch, void *stream) {
+    if (n_rows < 0 || (n_rows > 0 && !d_dists) || slope < 0 || slope > 2 || n_samples < 2)
+        return fail(PPB_ERR_ARG, "ppb_edges_from_dists_dev: bad argument");
+    ppb::PredDists pred{reinterpret_cast<const float2 *>(d_dists), slope, x_max, y_max};
+    return run_select(pred, n_rows, ppb::PairMap{1, n_samples, 0}, d_i, d_j, capacity, d_count, d_scratch,
+                      (cudaStream_t)stream);
+}
+
+int ppb_edges_from_labels_dev(const void *d_labels, int32_t label_dtype, int64_t n_rows, int32_t within_label,
+                              int32_t self, int64_t n_samples_or_num_ref, int64_t int_offset, int64_t *d_i,
+                              int64_t *d_j, int64_t capacity, int64_t *d_count, void *d_scratch, void *stream) {
+    if (n_rows < 0 || (n_rows > 0 && !d_labels) || n_samples_or_num_ref < 1)
+        return fail(PPB_ERR_ARG, "ppb_edges_from_labels_dev: bad argument");
+    const ppb::PairMap map{self, n_samples_or_num_ref, int_offset};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (label_dtype) {
+        case 0: return run_select(ppb::PredLabels<int8_t>{(const int8_t *)d_labels, within_label}, n_rows, map, d_i, d_j, capacity, d_count, d_scratch, st);
+        case 1: return run_select(ppb::PredLabels<int32_t>{(const int32_t *)d_labels, within_label}, n_rows, map, d_i, d_j, capacity, d_count, d_scratch, st);
+        case 2: return run_select(ppb::PredLabels<float>{(const float *)d_labels, within_label}, n_rows, map, d_i, d_j, capacity, d_count, d_scratch, st);
+        default: return fail(PPB_ERR_ARG, "ppb_edges_from_labels_dev: label_dtype must be 0 (int8), 1 (int32) or 2 (float32)");
+    }
+}
+
+int ppb_long_to_square_dev(const float *d_vec, int64_t stride, int64_t n, float *d_square, void *stream) {
+    if (n < 0 || stride < 1 || (n > 0 && !d_square) || (n > 1 && !d_vec))
+        return fail(PPB_ERR_ARG, "ppb_long_to_square_dev: bad argument");
+    if (n == 0) return PPB_OK;
+    ppb::long_to_square_kernel<<<grid_for(n * n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_vec, stride, n, d_square);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_square_to_long_dev(const float *d_square, int64_t n, float *d_vec, void *stream) {
+    if (n < 0 || (n > 1 && (!d_square || !d_vec))) return fail(PPB_ERR_ARG, "ppb_square_to_long_dev: bad argument");
+    if (n < 2) return PPB_OK;
+    ppb::square_to_long_kernel<<<grid_for(n * (n - 1) / 2, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_square, n, d_vec);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_long_to_square_multi_dev(const float *d_rr, int64_t stride_rr, const float *d_qr, int64_t stride_qr,
+                                 const float *d_qq, int64_t stride_qq, int64_t n_ref, int64_t n_qry, float *d_square,
+                                 void *stream) {
+    if (n_ref < 0 || n_qry < 0 || !d_square || stride_rr < 1 || stride_qr < 1 || stride_qq < 1 ||
+        (n_ref > 1 && !d_rr) || (n_ref > 0 && n_qry > 0 && !d_qr) || (n_qry > 1 && !d_qq))
+        return fail(PPB_ERR_ARG, "ppb_long_to_square_multi_dev: bad argument");
+    const int64_t n = n_ref + n_qry;
+    if (n == 0) return PPB_OK;
+    ppb::long_to_square_multi_kernel<<<grid_for(n * n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        d_rr, stride_rr, d_qr, stride_qr, d_qq, stride_qq, n_ref, n_qry, d_square);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
 }
 
 int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, float x_max, float y_max,

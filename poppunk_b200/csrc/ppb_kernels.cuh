@@ -78,6 +78,11 @@ struct QueryParams {
     int32_t n_peer_out;
     void *mc_out;
     int32_t stream_stores;  // 1: outputs are written evict-first (st.global.cs)
+    // fused edge list (N1): global row indices of pairs on the within side of the boundary, appended unordered
+    int32_t edge_mode;      // 0 off, 1: line_dist < 0 (assign == -1), 2: line_dist <= 0 (edge_iterate)
+    long long *edge_rows;
+    long long edge_cap;
+    unsigned long long *edge_count;
     int32_t a_policy, b_policy;  // L2 eviction priority of row-genome loads / column-genome TMA (0 normal, 1 last, 2 first)
     int8_t *labels;
     int32_t has_boundary;
@@ -225,7 +230,8 @@ struct RowInfo {
     int32_t i_ok;        // row genome exists
 };
 
-__device__ __forceinline__ void store_pair(const QueryParams &p, double sy, double sxy, int n, long long row) {
+// returns true when the pair is on the within side of the boundary (fused edge list)
+__device__ __forceinline__ bool store_pair(const QueryParams &p, double sy, double sxy, int n, long long row) {
     float core = 0.0f, acc = 0.0f;
     if (n >= 2) {
         const double beta = (sxy - p.xbar[n] * sy) * p.inv_sxx[n];  // slope     = log(1 - core)
@@ -250,9 +256,11 @@ __device__ __forceinline__ void store_pair(const QueryParams &p, double sy, doub
     if (p.has_boundary) {
         // models.py:1085-1089: assignThreshold(X / self.scale, slope, x_max, y_max)
         const float x0 = __fdiv_rn(core, p.bnd.scale_x), y0 = __fdiv_rn(acc, p.bnd.scale_y);
-        __stcs(reinterpret_cast<signed char *>(p.labels) + row,
-               (signed char)boundary_side(line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope)));
+        const float side = line_dist(x0, y0, p.bnd.x_max, p.bnd.y_max, p.bnd.slope);
+        if (p.labels) __stcs(reinterpret_cast<signed char *>(p.labels) + row, (signed char)boundary_side(side));
+        return p.edge_mode == 2 ? side <= 0.0f : side < 0.0f;
     }
+    return false;
 }
 
 // generic path: any output mode, logs computed in place (also the fallback when the y-table would be huge)
@@ -289,7 +297,7 @@ __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32
     }
     if (p.out_mode == PPB_OUT_JACCARD) return;
     degenerate = n < 2;
-    store_pair(p, sy, sxy, n, row);
+    (void)store_pair(p, sy, sxy, n, row);
 }
 
 
@@ -349,9 +357,19 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
                 const long long row = ri.row_base + j;
                 const bool ok = ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
                                 row < p.row_end - p.row_begin;
+                bool within = false;
                 if (ok) {
-                    store_pair(p, sy[r], sxy[r], n[r], row);
+                    within = store_pair(p, sy[r], sxy[r], n[r], row);
                     n_deg += n[r] < 2;
+                }
+                if (p.edge_mode) {  // warp-aggregated append of the global row index
+                    const uint32_t b = __ballot_sync(0xffffffffu, within);
+                    if (b) {
+                        unsigned long long at = 0;
+                        if (lane == 0) at = atomicAdd(p.edge_count, (unsigned long long)__popc(b));
+                        at = __shfl_sync(0xffffffffu, at, 0) + __popc(b & ((1u << lane) - 1));
+                        if (within && at < (unsigned long long)p.edge_cap) p.edge_rows[at] = row + p.row_begin;
+                    }
                 }
             }
         } else {

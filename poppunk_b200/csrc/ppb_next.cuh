@@ -1,0 +1,210 @@
+// "Next" rows of SURVEY.md section 8(f): the immediate consumers of the distance path.
+//
+//   N1  edge lists after the threshold (src/boundary.cpp:82-123: edge_iterate, generate_tuples):
+//       ordered stream compaction of the rows that pass a predicate, mapped to (i, j) sample pairs
+//   N2  long <-> square reshapes of the path's output (pp_sketchlib.longToSquare / squareToLong /
+//       longToSquareMulti; call sites PopPUNK/utils.py:393-405, network.py:2133-2134, models.py:1217,1357)
+//
+// All memory-bound index work: coalesced loads, warp ballots for ranking, no atomics on the ordered path.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ppb_kernels.cuh"
+
+namespace ppb {
+
+// ---- row -> (i, j): src/boundary.cpp:22-31 with an exact integer fix-up of the double sqrt ---------------
+__device__ __forceinline__ int64_t dev_sq2cond(int64_t i, int64_t j, int64_t n) {
+    return n * i - ((i * (i + 1)) >> 1) + j - 1 - i;
+}
+__device__ __forceinline__ int64_t dev_row_idx(int64_t k, int64_t n) {
+    const double d = sqrt((double)(-8 * k + 4 * n * (n - 1) - 7));
+    int64_t i = n - 2 - (int64_t)floor(d / 2.0 - 0.5);
+    i = max((int64_t)0, min(i, n - 2));
+    while (i > 0 && dev_sq2cond(i, i + 1, n) > k) i--;
+    while (i < n - 2 && dev_sq2cond(i + 1, i + 2, n) <= k) i++;
+    return i;
+}
+__device__ __forceinline__ int64_t dev_col_idx(int64_t k, int64_t i, int64_t n) {
+    return k + i + 1 - n * (n - 1) / 2 + (n - i) * ((n - i) - 1) / 2;
+}
+
+struct PairMap {
+    int32_t self;
+    int64_t n;           // self: number of samples; non-self: num_ref
+    int64_t int_offset;  // boundary.cpp:97-123 generate_tuples
+};
+__device__ __forceinline__ void row_to_pair(const PairMap &m, int64_t row, int64_t &i, int64_t &j) {
+    if (m.self) {
+        i = dev_row_idx(row, m.n);
+        j = dev_col_idx(row, i, m.n) + m.int_offset;
+        i += m.int_offset;
+    } else {  // boundary.cpp:112-113
+        i = row % m.n + m.int_offset;
+        j = row / m.n + m.n + m.int_offset;
+    }
+    if (i > j) {
+        const int64_t t = i;
+        i = j;
+        j = t;
+    }
+}
+
+// ---- predicates -------------------------------------------------------------------------------------------
+struct PredDists {  // edge_iterate: line_dist(...) <= 0   (boundary.cpp:82-95)
+    const float2 *d;
+    int32_t slope;
+    float x_max, y_max;
+    __device__ __forceinline__ bool operator()(int64_t row) const {
+        const float2 v = d[row];
+        return line_dist(v.x, v.y, x_max, y_max, slope) <= 0.0f;
+    }
+};
+template <typename T>
+struct PredLabels {  // generate_tuples: assignments[row] == within_label   (boundary.cpp:106)
+    const T *labels;
+    int32_t within;
+    __device__ __forceinline__ bool operator()(int64_t row) const { return (int32_t)labels[row] == within; }
+};
+
+// ---- ordered compaction -----------------------------------------------------------------------------------
+// A block owns kSelBlockRows consecutive rows; a warp owns kSelIters runs of 32 consecutive rows, so one ballot
+// per run already is the order.  Pass 0 writes the block's count; after an exclusive scan of the counts
+// (scan_kernel) pass 1 writes the pairs at their final position.  The predicate is evaluated once per pass.
+constexpr int kSelThreads = 256;
+constexpr int kSelIters = 16;
+constexpr int kSelBlockRows = kSelThreads * kSelIters;  // 4096
+
+template <typename Pred>
+__global__ void __launch_bounds__(kSelThreads) select_kernel(Pred pred, int64_t n_rows, PairMap map, int pass,
+                                                             int64_t *__restrict__ block_off, int64_t capacity,
+                                                             int64_t *__restrict__ out_i, int64_t *__restrict__ out_j) {
+    __shared__ uint32_t warp_tot[kSelThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t base = (int64_t)blockIdx.x * kSelBlockRows + (int64_t)warp * (32 * kSelIters);
+    uint32_t ballots[kSelIters];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int m = 0; m < kSelIters; m++) {
+        const int64_t row = base + m * 32 + lane;
+        const bool sel = row < n_rows && pred(row);
+        ballots[m] = __ballot_sync(0xffffffffu, sel);
+        tot += __popc(ballots[m]);
+    }
+    if (lane == 0) warp_tot[warp] = tot;
+    __syncthreads();
+    uint32_t before = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; w++) {
+        before += w < warp ? warp_tot[w] : 0;
+        block_total += warp_tot[w];
+    }
+    if (pass == 0) {
+        if (threadIdx.x == 0) block_off[blockIdx.x] = block_total;
+        return;
+    }
+    int64_t pos = block_off[blockIdx.x] + before;
+#pragma unroll
+    for (int m = 0; m < kSelIters; m++) {
+        const uint32_t b = ballots[m];
+        if (b & (1u << lane)) {
+            const int64_t at = pos + __popc(b & ((1u << lane) - 1));
+            if (at < capacity) {
+                int64_t i, j;
+                row_to_pair(map, base + m * 32 + lane, i, j);
+                out_i[at] = i;
+                out_j[at] = j;
+            }
+        }
+        pos += __popc(b);
+    }
+}
+
+// exclusive scan of int64 counts in place (one CTA; the array is n_rows/4096 long), total -> *d_total
+__global__ void __launch_bounds__(1024) scan_kernel(int64_t *__restrict__ a, int64_t n, int64_t *__restrict__ d_total) {
+    __shared__ int64_t warp_sum[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t start = 0; start < n; start += 1024) {
+        const int64_t idx = start + threadIdx.x;
+        const int64_t v = idx < n ? a[idx] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t s = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sum[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t incl = x + (warp ? warp_sum[warp - 1] : 0) + carry;
+        if (idx < n) a[idx] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *d_total = carry_s;
+}
+
+__global__ void rows_to_pairs_kernel(const int64_t *__restrict__ rows, int64_t n, PairMap map,
+                                     int64_t *__restrict__ out_i, int64_t *__restrict__ out_j) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i, j;
+        row_to_pair(map, rows[r], i, j);
+        out_i[r] = i;
+        out_j[r] = j;
+    }
+}
+
+// ---- N2: long <-> square -----------------------------------------------------------------------------------
+// vec is read with an element stride (PopPUNK passes column views distMat[:, [c]] of the (n_pairs, 2) array).
+__global__ void long_to_square_kernel(const float *__restrict__ vec, int64_t stride, int64_t n,
+                                      float *__restrict__ sq) {
+    const int64_t total = n * n;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = o / n, c = o - r * n;
+        sq[o] = r == c ? 0.0f : vec[dev_sq2cond(min(r, c), max(r, c), n) * stride];
+    }
+}
+__global__ void square_to_long_kernel(const float *__restrict__ sq, int64_t n, float *__restrict__ vec) {
+    const int64_t total = n * (n - 1) / 2;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = dev_row_idx(k, n), j = dev_col_idx(k, i, n);
+        vec[k] = sq[i * n + j];
+    }
+}
+// (R+Q)^2 square from: condensed ref-ref, query-major query-ref rectangle, condensed query-query
+__global__ void long_to_square_multi_kernel(const float *__restrict__ rr, int64_t s_rr, const float *__restrict__ qr,
+                                            int64_t s_qr, const float *__restrict__ qq, int64_t s_qq, int64_t R,
+                                            int64_t Q, float *__restrict__ sq) {
+    const int64_t n = R + Q, total = n * n;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = o / n, c = o - r * n;
+        const int64_t lo = min(r, c), hi = max(r, c);
+        float v = 0.0f;
+        if (lo != hi) {
+            if (hi < R)
+                v = rr[dev_sq2cond(lo, hi, R) * s_rr];
+            else if (lo >= R)
+                v = qq[dev_sq2cond(lo - R, hi - R, Q) * s_qq];
+            else
+                v = qr[((hi - R) * R + lo) * s_qr];  // row = q*R + r (utils.py:224-226)
+        }
+        sq[o] = v;
+    }
+}
+
+}  // namespace ppb

@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import OUT_COUNTS, OUT_DISTS, OUT_JACCARD, BBITS, Boundary, check
 
 __all__ = ["PackedSketches", "pack", "query", "query_host", "assign_threshold", "num_rows", "shard_rows",
-           "query_sharded", "FusedExchange", "OUT_DISTS", "OUT_JACCARD", "OUT_COUNTS"]
+           "query_sharded", "query_edges", "FusedExchange", "OUT_DISTS", "OUT_JACCARD", "OUT_COUNTS"]
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -279,6 +279,54 @@ def query_sharded(ref: PackedSketches, qry: Optional[PackedSketches], kmers, ran
     dist.all_gather_into_tensor(full, mine, group=group)
     dist.all_reduce(ndeg, group=group)
     return full[:total], ndeg
+
+
+def query_edges(ref: PackedSketches, qry: Optional[PackedSketches], kmers, boundary, rand_table=None,
+                row_begin: int = 0, row_end: Optional[int] = None, include_boundary: bool = False,
+                capacity: Optional[int] = None, int_offset: int = 0, sort: bool = True):
+    """Distances -> boundary test -> edge list in ONE kernel pass: nothing of size n_pairs is written.
+
+    The fused form of ``queryDatabase`` + ``model.assign`` + ``generateTuples`` (assign.py:502-510, 593-601,
+    network.py:1180-1184): returns ``(i, j, n_edges, n_degenerate)`` with int64 device tensors of the
+    within-boundary pairs (``line_dist < 0``, or ``<= 0`` with ``include_boundary`` as edge_iterate does),
+    in the reference's row order when ``sort`` (the kernel appends unordered).  ``n_edges`` may exceed
+    ``capacity`` (default: 1/8 of the rows, at least 1 Mi) — then only ``capacity`` edges were kept."""
+    L = _lib.load()
+    dev = _require_cuda(ref.device)
+    self_mode = qry is None
+    kmers_np = np.ascontiguousarray(kmers, dtype=np.int32)
+    total = num_rows(ref.n, None if self_mode else qry.n)
+    if row_end is None:
+        row_end = total
+    rows = row_end - row_begin
+    if capacity is None:
+        capacity = max(1 << 20, rows // 8)
+    capacity = max(1, min(capacity, max(rows, 1)))
+    bnd = _boundary(boundary)
+    tab, C_ = None, 0
+    if rand_table is not None:
+        tab = torch.as_tensor(rand_table, dtype=torch.float32).to(dev).contiguous()
+        C_ = tab.shape[0]
+    edge_rows = torch.empty(capacity, dtype=torch.int64, device=dev)
+    n_edges = torch.zeros(1, dtype=torch.int64, device=dev)
+    ndeg = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(L.ppb_query_edges_dev(
+            ref.data.data_ptr(), ref.n, None if self_mode else qry.data.data_ptr(), 0 if self_mode else qry.n,
+            kmers_np.ctypes.data, ref.K, ref.sketchsize64, tab.data_ptr() if tab is not None else None, C_,
+            ref.clusters.data_ptr() if tab is not None else None,
+            qry.clusters.data_ptr() if (tab is not None and not self_mode) else None,
+            row_begin, row_end, C.byref(bnd), int(include_boundary), edge_rows.data_ptr(), capacity,
+            n_edges.data_ptr(), None, None, ndeg.data_ptr(), _stream_ptr(dev)), "ppb_query_edges_dev")
+        n = int(n_edges.item())
+        kept = edge_rows[:min(n, capacity)]
+        if sort:
+            kept = torch.sort(kept).values          # plumbing: restores the reference's row order
+        oi = torch.empty_like(kept)
+        oj = torch.empty_like(kept)
+        check(L.ppb_rows_to_pairs_dev(kept.data_ptr(), kept.numel(), int(self_mode), ref.n, int(int_offset),
+                                      oi.data_ptr(), oj.data_ptr(), _stream_ptr(dev)), "ppb_rows_to_pairs_dev")
+    return oi, oj, n, int(ndeg.item())
 
 
 class FusedExchange:

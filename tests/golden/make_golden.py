@@ -10,7 +10,8 @@ Fixtures written next to this file:
   json_sketch.npz      the reference's only real pp-sketchlib sketch (test/json_sketch.txt): pins the
                        sketch schema W = sketchsize64*bbits, bbits = 14
   refine_grid.npz      test/test-refine.py:46-61 — 10x10 float32 grid, boundary (0.5, 0.5), slopes 0/1/2,
-                       labels from the reference's own ``withinBoundary`` restatement (:10-23)
+                       labels from the reference's own ``withinBoundary`` restatement (:10-23), and the edge
+                       lists its ``iter_tuples`` loop (:30-38) derives from them for a seeded 100-sample cloud
   fit_kmer_curve.npz   PopPUNK/sketchlib.py:635-670 ``fitKmerCurve`` (scipy bounded least squares) run on
                        seeded per-k Jaccard vectors: pins model, clamp and (core, acc) output order
 """
@@ -56,8 +57,13 @@ def refine_grid():
     rng = np.random.default_rng(7)
     cloud = rng.random((4950, 2)).astype(np.float32)
     cloud_labels = np.stack([within(cloud, 0.5, 0.5, s) for s in (0, 1, 2)]).astype(np.float32)
+    # edge lists the reference test expects from generateTuples / edgeThreshold (test-refine.py:30-38, 64-82):
+    # its own Python loop over the condensed rows of 100 samples
+    iter_tuples = extract_function(os.path.join(REF, "test", "test-refine.py"), "iter_tuples", {})
+    edges = {f"cloud_edges_{s}": np.array(iter_tuples(cloud_labels[s], 100), dtype=np.int64).reshape(-1, 2)
+             for s in (0, 1, 2)}
     np.savez_compressed(os.path.join(HERE, "refine_grid.npz"), dist=dist, labels=labels, cloud=cloud,
-                        cloud_labels=cloud_labels, x_max=np.float32(0.5), y_max=np.float32(0.5))
+                        cloud_labels=cloud_labels, x_max=np.float32(0.5), y_max=np.float32(0.5), **edges)
     print("refine_grid:", dist.shape, labels.shape, [int((l == -1).sum()) for l in labels])
 
 

@@ -1,0 +1,97 @@
+"""GPU tests of the "next" rows: N1 edge lists, N2 long<->square reshapes."""
+import os
+
+import numpy as np
+import pytest
+
+from poppunk_b200 import synth
+
+pytestmark = pytest.mark.gpu
+KMERS = np.array([15, 19, 23, 27, 31], dtype=np.int32)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    from poppunk_b200 import engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def test_edges_golden_test_refine(eng, golden_dir):
+    """test/test-refine.py:64-82: generateTuples / edgeThreshold vs the reference's own Python loop (golden)."""
+    from poppunk_b200 import refine
+    g = np.load(os.path.join(golden_dir, "refine_grid.npz"))
+    for slope in (0, 1, 2):
+        exp = [tuple(x) for x in g[f"cloud_edges_{slope}"].tolist()]
+        labels = g["cloud_labels"][slope]
+        assert refine.generateTuples([int(x) for x in labels], -1) == exp
+        assert refine.generateTuples(labels.astype(np.int8), -1) == exp
+        assert refine.generateTuples(labels.astype(np.float32), -1) == exp
+        # edge_iterate keeps rows with line_dist <= 0: a superset that adds the rows labelled 0
+        got = refine.edgeThreshold(g["cloud"], slope, 0.5, 0.5)
+        assert set(exp) <= set(got) and len(got) == int((labels <= 0).sum())
+        assert got == sorted(got)                      # row order == lexicographic (i, j) in self mode
+
+
+def test_edges_vs_oracle_large_and_rect(eng, oracle):
+    from poppunk_b200 import refine
+    rng = np.random.default_rng(3)
+    n = 1500
+    d = rng.random((n * (n - 1) // 2, 2)).astype(np.float32)
+    for slope, xm, ym in ((2, 0.3, 0.2), (0, 0.05, 0.0), (1, 0.0, 0.9)):
+        oi, oj = oracle.edge_iterate(d, slope, xm, ym)
+        assert refine.edgeThreshold(d, slope, xm, ym) == list(zip(oi.tolist(), oj.tolist()))
+    lab = rng.integers(-1, 2, size=37 * 211).astype(np.int32)
+    oi, oj = oracle.generate_tuples(lab, -1, self=False, num_ref=211, int_offset=5)
+    assert refine.generateTuples(lab, -1, self=False, num_ref=211, int_offset=5) == list(zip(oi.tolist(), oj.tolist()))
+    assert refine.generateTuples(np.zeros(0, dtype=np.int32), -1) == []
+    assert refine.generateTuples(np.ones(10, dtype=np.int32), -1) == []
+
+
+def test_fused_query_edges(eng, oracle):
+    """distances -> threshold -> edges in one kernel == oracle distances + assign_threshold + generate_tuples."""
+    import torch
+    ref, qry = synth.synth_sketches(300, KMERS, 16, seed=1), synth.synth_sketches(90, KMERS, 16, seed=1, sample_seed=1)
+    pr, pq = eng.pack(ref), eng.pack(qry)
+    bnd = (2, 0.02, 0.2, 1.0, 1.0)
+    for q_np, q_pk in ((None, None), (qry, pq)):
+        d_o, lab_o, _ = oracle.query(ref, q_np, KMERS, boundary=bnd)
+        oi, oj = oracle.generate_tuples(lab_o.astype(np.int32), -1, self=q_np is None, num_ref=300)
+        gi, gj, n, _ = eng.query_edges(pr, q_pk, KMERS, bnd)
+        torch.cuda.synchronize()
+        assert n == len(oi) and n > 100
+        assert (gi.cpu().numpy() == oi).all() and (gj.cpu().numpy() == oj).all()
+    # row shards concatenate to the same list; <= 0 variant is a superset
+    total = eng.num_rows(300)
+    parts = [eng.query_edges(pr, None, KMERS, bnd, row_begin=b, row_end=e) for b, e in ((0, 20000), (20000, total))]
+    oi, oj = oracle.generate_tuples(oracle.query(ref, None, KMERS, boundary=bnd)[1].astype(np.int32), -1)
+    assert (torch.cat([p[0] for p in parts]).cpu().numpy() == oi).all()
+    _, _, n_le, _ = eng.query_edges(pr, None, KMERS, bnd, include_boundary=True)
+    assert n_le >= len(oi)
+    # capacity overflow is reported, not written past
+    gi, gj, n, _ = eng.query_edges(pr, None, KMERS, bnd, capacity=10)
+    assert n == len(oi) and gi.numel() == 10
+
+
+def test_long_square_roundtrip(eng, oracle):
+    from poppunk_b200 import reshape
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 17, 400):
+        v = rng.random(n * (n - 1) // 2).astype(np.float32)
+        sq = reshape.longToSquare(distVec=v.reshape(-1, 1), num_threads=2)
+        assert (sq == oracle.long_to_square(v, n)).all()
+        assert (sq == sq.T).all() and (np.diag(sq) == 0).all()
+        assert (reshape.squareToLong(sq, 2) == v).all()
+    R, Q = 23, 9
+    rr, qr, qq = (rng.random(m).astype(np.float32) for m in (R * (R - 1) // 2, R * Q, Q * (Q - 1) // 2))
+    m = reshape.longToSquareMulti(distVec=rr.reshape(-1, 1), query_ref_distVec=qr.reshape(-1, 1),
+                                  query_query_distVec=qq.reshape(-1, 1), num_threads=1)
+    assert (m == oracle.long_to_square_multi(rr, qr, qq, R, Q)).all()
+    assert m[R + 2, 5] == qr[2 * R + 5] and m[5, R + 2] == qr[2 * R + 5]     # row = q*R + r
+    # a column of the engine's own (n_pairs, 2) output, as PopPUNK passes it (utils.py:393-396)
+    ref = synth.synth_sketches(40, KMERS, 4, seed=2)
+    d, _, _ = eng.query_host(ref, None, KMERS)
+    core = reshape.longToSquare(distVec=d[:, [0]], num_threads=1)
+    i, j = np.triu_indices(40, k=1)
+    assert (core[i, j] == d[:, 0]).all()

@@ -233,3 +233,34 @@ def test_assign_threshold_vs_numpy(oracle):
     scaled = (dist / np.array([0.9, 0.8], dtype=np.float32)).astype(np.float32)
     assert (labels == oracle.assign_threshold(scaled, 2, 0.02, 0.2).astype(np.int8)).all()
     assert set(np.unique(labels)) <= {-1, 0, 1} and (labels == -1).any() and (labels == 1).any()
+
+
+# ---------------------------------------------------------------- "next" rows N1 / N2 (oracle pinned on CPU)
+def test_edges_oracle_vs_reference_loop(oracle, golden_dir):
+    """Golden edge lists from the reference test's own Python loop (test/test-refine.py:30-38, 64-82)."""
+    g = np.load(os.path.join(golden_dir, "refine_grid.npz"))
+    for slope in (0, 1, 2):
+        exp = g[f"cloud_edges_{slope}"]
+        oi, oj = oracle.generate_tuples(g["cloud_labels"][slope].astype(np.int32), -1)
+        assert (np.stack([oi, oj], axis=1) == exp).all()
+        ei, ej = oracle.edge_iterate(g["cloud"], slope, 0.5, 0.5)       # <= 0: adds rows labelled 0
+        assert len(ei) == int((g["cloud_labels"][slope] <= 0).sum())
+        assert set(map(tuple, exp.tolist())) <= set(zip(ei.tolist(), ej.tolist()))
+    lab = np.array([-1, 0, -1, 1, -1, -1], dtype=np.int32)             # 2 refs x 3 queries, row = q*R + r
+    oi, oj = oracle.generate_tuples(lab, -1, self=False, num_ref=2, int_offset=10)
+    assert list(zip(oi.tolist(), oj.tolist())) == [(10, 12), (10, 13), (10, 14), (11, 14)]
+
+
+def test_long_square_oracle(oracle):
+    rng = np.random.default_rng(1)
+    n = 31
+    v = rng.random(n * (n - 1) // 2).astype(np.float32)
+    sq = oracle.long_to_square(v, n)
+    i, j = np.triu_indices(n, k=1)
+    assert (sq[i, j] == v).all() and (sq == sq.T).all() and (np.diag(sq) == 0).all()
+    assert (oracle.square_to_long(sq) == v).all()
+    R, Q = 6, 4
+    rr, qr, qq = (rng.random(m).astype(np.float32) for m in (15, 24, 6))
+    m = oracle.long_to_square_multi(rr, qr, qq, R, Q)
+    assert (m[:R, :R] == oracle.long_to_square(rr, R)).all() and (m[R:, R:] == oracle.long_to_square(qq, Q)).all()
+    assert (m[R:, :R] == qr.reshape(Q, R)).all() and (m == m.T).all()
