@@ -285,6 +285,7 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (const char *e = std::getenv("PPB_STREAM_STORES")) p.stream_stores = atoi(e);
     if (const char *e = std::getenv("PPB_A_POLICY")) p.a_policy = atoi(e);
     if (const char *e = std::getenv("PPB_B_POLICY")) p.b_policy = atoi(e);
+    if (const char *e = std::getenv("PPB_DEBUG_SKIP_EPILOGUE")) p.debug_skip_epilogue = atoi(e);
 
     TileKey key{dev, p.nA, p.nB, self, tj, 0, 0, band};
     if (self) {

@@ -83,6 +83,7 @@ struct QueryParams {
     long long *edge_rows;
     long long edge_cap;
     unsigned long long *edge_count;
+    int32_t debug_skip_epilogue;  // measurement only (PPB_DEBUG_SKIP_EPILOGUE): epilogue warps do no work
     int32_t a_policy, b_policy;  // L2 eviction priority of row-genome loads / column-genome TMA (0 normal, 1 last, 2 first)
     int8_t *labels;
     int32_t has_boundary;
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
             const uint32_t b = lt % kCntBufs, ph = (lt / kCntBufs) & 1;
             mbar_wait_relaxed(&cfull[b], ph, 500);
             const uint32_t *cnt = reinterpret_cast<const uint32_t *>(smem + L.off_cnt + b * L.cnt_bytes);
-            tile_epilogue(p, cnt, rinfo, (int64_t)tc.x * kTI, (int64_t)tc.y * tj, et, lane);
+            if (!p.debug_skip_epilogue) tile_epilogue(p, cnt, rinfo, (int64_t)tc.x * kTI, (int64_t)tc.y * tj, et, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&cempty[b]);
             bar_sync(2, kEpiWarps * 32);  // rinfo is rewritten by the next tile
