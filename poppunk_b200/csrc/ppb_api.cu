@@ -494,18 +494,23 @@ int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, flo
 }
 
 int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *lane_ops, void *stream) {
-    if (mode < 0 || mode > 3 || iters < 1 || !d_sink) return fail(PPB_ERR_ARG, "ppb_microbench_dev: bad argument");
+    const bool half_occupancy = mode >= 10;  // 10+m: mode m with ONE 256-thread CTA per SM (2 warps per scheduler)
+    if (half_occupancy) mode -= 10;
+    if (mode < 0 || mode > 6 || iters < 1 || !d_sink) return fail(PPB_ERR_ARG, "ppb_microbench_dev: bad argument");
     int dev = 0, sms = 0;
     PPB_CUDA(cudaGetDevice(&dev));
     if (int rc = num_sms(dev, &sms)) return rc;
-    const unsigned grid = sms * 2, threads = 256;
+    const unsigned grid = half_occupancy ? sms : sms * 2, threads = 256;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t per_thread_iter = 0;
     switch (mode) {
         case 0: ppb::microbench_kernel<0><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
         case 1: ppb::microbench_kernel<1><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
         case 2: ppb::microbench_kernel<2><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
-        default: ppb::microbench_kernel<3><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 8; break;
+        case 3: ppb::microbench_kernel<3><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 8; break;
+        case 4: ppb::microbench_kernel<4><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
+        case 5: ppb::microbench_kernel<5><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
+        default: ppb::microbench_kernel<6><<<grid, threads, 0, st>>>(iters, d_sink, 12345u); per_thread_iter = 112; break;
     }
     g_launches++;
     PPB_CUDA(cudaGetLastError());

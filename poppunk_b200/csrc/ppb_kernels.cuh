@@ -322,6 +322,12 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
     const int ewarp = et >> 5;
     const int n_units = (kTI / 4) * tj / 32;
     const bool fast = p.ytab != nullptr;
+    // interior tile: every (i, j) of it is a real pair inside the row shard -> no per-pair tests
+    bool interior = i0 + kTI <= p.nA && j0 + tj <= p.nB && (!p.self || i0 + kTI - 1 < j0);
+    if (interior) {
+        const long long first = rinfo[0].row_base + j0, last = rinfo[kTI - 1].row_base + j0 + tj - 1;
+        interior = first >= 0 && last < p.row_end - p.row_begin;
+    }
     uint32_t n_deg = 0;
     for (int u = ewarp; u < n_units; u += kEpiWarps) {
         const int flat = u * 32 + lane;
@@ -330,34 +336,44 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
         const bool j_ok = j < p.nB;
         const uint32_t *cnt_col = cnt + jl * kCntRowWords + (il0 >> 1);
         if (fast) {
+            // Written to stay off the ALU pipe (it belongs to the compute warps sharing the scheduler): counts
+            // come in as 16-bit loads, table addresses are formed with IMAD / IMAD.WIDE, the series is folded with
+            // predicated FP64 adds, and interior tiles skip every per-pair bounds test.
             const int32_t col_off = (p.rand_table && j_ok) ? (int32_t)p.clB[j] * p.C * K * S1 : 0;
             double sy[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
             int n[4] = {0, 0, 0, 0};
             bool open[4] = {true, true, true, true};
-            int32_t off[4];
+            const double *yrow[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) off[r] = col_off + rinfo[il0 + r].ytab_off;
+            for (int r = 0; r < 4; r++) yrow[r] = p.ytab + (col_off + rinfo[il0 + r].ytab_off);
+            const uint16_t *c16 = reinterpret_cast<const uint16_t *>(cnt_col);
 #pragma unroll 5
             for (int t = 0; t < K; t++) {
-                const uint2 w = *reinterpret_cast<const uint2 *>(cnt_col + t * tj * kCntRowWords);
-                const uint32_t c[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
                 const double x = p.x[t];
+                const uint32_t tS1 = (uint32_t)(t * S1);
+                double y[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    const double y = __ldg(p.ytab + (off[r] + t * S1 + (int32_t)c[r]));
-                    open[r] = open[r] && (y <= 0.0);  // the first k with J < 5/S ends the series
-                    const double ym = open[r] ? y : 0.0;
-                    sy[r] += ym;
-                    sxy[r] = fma(x, ym, sxy[r]);
-                    n[r] += open[r] ? 1 : 0;
+                    uint32_t e;  // c + t*(S+1) as an IMAD (FMA pipe)
+                    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(e) : "r"((uint32_t)c16[t * tj * (kCntRowWords * 2) + r]), "r"(tS1));
+                    y[r] = __ldg(yrow[r] + e);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    open[r] = open[r] && (y[r] <= 0.0);  // the first k with J < 5/S ends the series
+                    if (open[r]) {
+                        sy[r] += y[r];
+                        sxy[r] = fma(x, y[r], sxy[r]);
+                        n[r]++;
+                    }
                 }
             }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const RowInfo ri = rinfo[il0 + r];
                 const long long row = ri.row_base + j;
-                const bool ok = ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
-                                row < p.row_end - p.row_begin;
+                const bool ok = interior || (ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
+                                             row < p.row_end - p.row_begin);
                 bool within = false;
                 if (ok) {
                     within = store_pair(p, sy[r], sxy[r], n[r], row);
@@ -613,7 +629,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) microbench_kernel(int64_t iters, uint32_t *sink, uint32_t seed) {
-    uint32_t x[8], av[14], acc = 0;
+    uint32_t x[8], av[14], acc = 0, y[4] = {1, 2, 3, 4};
+    float f[4] = {1.f, 2.f, 3.f, 4.f};
 #pragma unroll
     for (int g = 0; g < 8; g++) x[g] = seed * (threadIdx.x + 1) + g * 0x9e3779b9u;
 #pragma unroll
@@ -637,11 +654,29 @@ __global__ void __launch_bounds__(256, 2) microbench_kernel(int64_t iters, uint3
                 for (int r = 0; r < 14; r++) bits = and_xnor(bits, av[r], x[g]);
                 x[g] += __popc(bits);
             }
-        } else {  // MODE 3: warp REDUX
+        } else if (MODE == 3) {  // warp REDUX
 #pragma unroll
             for (int g = 0; g < 8; g++) x[g] = __reduce_add_sync(0xffffffffu, x[g]);
+        } else {
+            // MODE 4/5/6: does a non-ALU instruction issued between LOP3s cost LOP3 throughput?
+            // 4 interleaved chains x 14 LOP3 (x2), plus per 14 LOP3: 4 IMAD (mode 4), 4 LDS (mode 5), 4 FFMA (mode 6)
+            __shared__ uint32_t sm[256 * 4];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+                for (int r = 0; r < 14; r++)
+#pragma unroll
+                    for (int g = 0; g < 4; g++) x[half * 4 + g] = and_xnor(x[half * 4 + g], av[r], av[(r + g) % 14]);
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    if (MODE == 4) y[e & 3] = y[e & 3] * 3u + av[e & 7];
+                    if (MODE == 5) y[e & 3] = reinterpret_cast<volatile uint32_t *>(sm)[threadIdx.x + (e & 3) * 256];
+                    if (MODE == 6) f[e & 3] = fmaf(f[e & 3], 1.0001f, 0.5f);
+                }
+            }
         }
     }
+    x[0] ^= y[0] ^ y[1] ^ y[2] ^ y[3] ^ __float_as_uint(f[0] + f[1] + f[2] + f[3]);
 #pragma unroll
     for (int g = 0; g < 8; g++) acc ^= x[g];
     if (acc == 0x12345678u) sink[0] = acc;  // keep the work alive
