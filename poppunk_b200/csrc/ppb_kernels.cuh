@@ -44,7 +44,7 @@ constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
 #define PPB_STAGES 6
 #endif
 #ifndef PPB_EPI_WARPS
-#define PPB_EPI_WARPS 2
+#define PPB_EPI_WARPS 4
 #endif
 #ifndef PPB_JJ_UNROLL
 #define PPB_JJ_UNROLL 4
@@ -54,8 +54,15 @@ constexpr int kStages = PPB_STAGES;
 constexpr int kJJUnroll = PPB_JJ_UNROLL;           // column-loop unroll inside a stage
 constexpr int kStageBytes = kJB * kSliceBytes;     // 7168
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
-constexpr int kEpiWarps = PPB_EPI_WARPS;           // epilogue warps (fit + stores), off the LOP3 critical path
-constexpr int kThreads = (kComputeWarps + 1 + kEpiWarps) * 32;  // + 1 TMA producer warp
+constexpr int kEpiWarps = PPB_EPI_WARPS;           // epilogue warps (fit + stores): one per scheduler, so all four are loaded alike
+constexpr int kProducerWarp = kComputeWarps + kEpiWarps;  // last warp: TMA producer
+constexpr int kThreads = (kComputeWarps + 2 * 4) * 32;  // 4 full warpgroups: setmaxnreg is a warpgroup-wide operation
+// 13 warps put four on scheduler 0, i.e. 128 registers per thread at launch; the warpgroups then trade registers
+// (setmaxnreg): helpers shrink, the two compute warpgroups grow back to what the register-stationary tile needs.
+// Conservation inside the CTA's pool: 8 x 168 + 8 x 88 = 2048 = 16 x 128 (warps 13-15 only give their registers back).
+constexpr int kRegsCompute = 168, kRegsHelper = 88;
+static_assert(kEpiWarps == 4 && kComputeWarps * kRegsCompute + 8 * kRegsHelper <= 16 * 128,
+              "setmaxnreg: the compute warps can only grow by what the helper warpgroups give back");
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
 constexpr int kCtasPerSM = 1;                      // measured: 2 x (4 warps, 32-row tiles) is slower (profiles/)
@@ -486,7 +493,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 
     const int tj = p.tj, n_jb = tj / kJB, KS = p.KS;
 
-    if (warp == kComputeWarps) {
+    if (warp >= kProducerWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
+        if (warp > kProducerWarp) return;  // filler warps of the producer's warpgroup
         // ===== TMA producer: streams column-genome slices of every (tile, k, slice) into the ring =====
         if (lane == 0) {
             const uint64_t pol_b = l2_policy(p.b_policy);
@@ -509,9 +518,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         return;
     }
 
-    if (warp > kComputeWarps) {
+    if (warp >= kComputeWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
         // ===== epilogue warps: fit + stores of tile t while the compute warps are already in tile t+1 =====
-        const int et = threadIdx.x - (kComputeWarps + 1) * 32;
+        const int et = threadIdx.x - kComputeWarps * 32;
         RowInfo *rinfo = reinterpret_cast<RowInfo *>(smem + L.off_rinfo);
         uint32_t lt = 0;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
@@ -528,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     }
 
     // ===== compute warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
     // Software pipeline over columns: while the LOP3 stream of column c runs, the packed partial counts of
     // column c-1 go through REDUX and are stored at the end — no POPC/REDUX latency is ever waited for.
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
