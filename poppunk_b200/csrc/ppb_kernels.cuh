@@ -59,9 +59,10 @@ constexpr int kProducerWarp = kComputeWarps + kEpiWarps;  // last warp: TMA prod
 constexpr int kThreads = (kComputeWarps + 2 * 4) * 32;  // 4 full warpgroups: setmaxnreg is a warpgroup-wide operation
 // 13 warps put four on scheduler 0, i.e. 128 registers per thread at launch; the warpgroups then trade registers
 // (setmaxnreg): helpers shrink, the two compute warpgroups grow back to what the register-stationary tile needs.
-// Conservation inside the CTA's pool: 8 x 168 + 8 x 88 = 2048 = 16 x 128 (warps 13-15 only give their registers back).
-constexpr int kRegsCompute = 168, kRegsHelper = 88;
-static_assert(kEpiWarps == 4 && kComputeWarps * kRegsCompute + 8 * kRegsHelper <= 16 * 128,
+// Conservation inside the CTA's pool: 8 x 168 + 4 x 88 + 4 x 24 <= 16 x 128 (warps 13-15 only give registers back;
+// the compute branch needs ~150, measured: 200 brings nothing).
+constexpr int kRegsCompute = 168, kRegsHelper = 88, kRegsProducer = 24;
+static_assert(kEpiWarps == 4 && kComputeWarps * kRegsCompute + 4 * kRegsHelper + 4 * kRegsProducer <= 16 * 128,
               "setmaxnreg: the compute warps can only grow by what the helper warpgroups give back");
 constexpr int kPad = 128;                          // genome padding of packed arrays
 constexpr int kMaxTJ = 128;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const int tj = p.tj, n_jb = tj / kJB, KS = p.KS;
 
     if (warp >= kProducerWarp) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
         if (warp > kProducerWarp) return;  // filler warps of the producer's warpgroup
         // ===== TMA producer: streams column-genome slices of every (tile, k, slice) into the ring =====
         if (lane == 0) {
