@@ -191,6 +191,12 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref,
                    const ppb_boundary *boundary, int8_t *labels,
                    int64_t *n_degenerate, int32_t device_id);
 
+/* How ppb_query_host cuts [row_begin,row_end) into launches: chunks of at most cap_rows rows that end on row-tile
+ * boundaries (64 genomes of the row side) whenever a whole row tile fits.  Writes up to max_chunks (begin,end)
+ * pairs into bounds (may be NULL) and returns the number of chunks, or -1 on a bad argument.  Host-only.     */
+int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,
+                             int64_t cap_rows, int64_t *bounds, int64_t max_chunks);
+
 /* Frees the device workspace the host-buffer calls keep between invocations (grow-only, per device). */
 int ppb_release_workspace(void);
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "ppb_assign_threshold_dev", "ppb_query_host", "ppb_assign_threshold_host", "ppb_microbench_dev",
     "ppb_launch_count", "ppb_release_workspace", "ppb_query_edges_dev", "ppb_rows_to_pairs_dev",
     "ppb_edges_scratch_bytes", "ppb_edges_from_dists_dev", "ppb_edges_from_labels_dev", "ppb_long_to_square_dev",
-    "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev",
+    "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev", "ppb_plan_host_chunks",
 ]
 
 
@@ -91,6 +91,8 @@ def load():
     L.ppb_square_to_long_dev.restype = C.c_int
     L.ppb_long_to_square_multi_dev.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, vp, vp]
     L.ppb_long_to_square_multi_dev.restype = C.c_int
+    L.ppb_plan_host_chunks.argtypes = [i64, i64, i32, i64, i64, i64, vp, i64]
+    L.ppb_plan_host_chunks.restype = i64
     L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]
     L.ppb_microbench_dev.restype = C.c_int
     _lib = L

@@ -130,6 +130,37 @@ int num_sms(int dev, int *out) {
 
 int out_row_bytes(int mode, int K) { return mode == PPB_OUT_DISTS ? 8 : 4 * K; }
 
+// Row chunks of the host-buffer path: cut [row_begin, row_end) into pieces of at most `cap` rows that end on
+// row-TILE boundaries (kTI genomes of the row side) wherever a whole row tile fits under the cap.
+void plan_chunks(int64_t n_ref, int64_t n_qry, int self, int64_t row_begin, int64_t row_end, int64_t cap,
+                 std::vector<std::pair<int64_t, int64_t>> *chunks) {
+    const int64_t n_side = self ? n_ref : n_qry;
+    const int64_t total_rows = self ? n_ref * (n_ref - 1) / 2 : n_ref * n_qry;
+    // first output row of row-side genome g (self: condensed row of (g, g+1); non-self: g * n_ref)
+    auto first_row_of = [&](int64_t g) -> int64_t {
+        if (g >= (self ? n_side - 1 : n_side)) return total_rows;
+        return self ? sq2cond(g, g + 1, n_ref) : g * n_ref;
+    };
+    const int64_t n_row_tiles = (n_side + ppb::kTI - 1) / ppb::kTI;
+    auto tile_end = [&](int64_t t) { return std::min(row_end, first_row_of(t * ppb::kTI)); };  // monotonic in t
+    for (int64_t r0 = row_begin; r0 < row_end;) {
+        const int64_t g0 = self ? row_idx(r0, n_ref) : r0 / n_ref;
+        int64_t lo = g0 / ppb::kTI + 1, r1;
+        if (tile_end(lo) > r0 + cap) {
+            r1 = std::min(row_end, r0 + cap);  // one row tile alone exceeds the cap (n > ~1M): cut inside it
+        } else {
+            int64_t hi = std::max(lo, n_row_tiles);  // last boundary t with tile_end(t) <= r0 + cap
+            while (lo < hi) {
+                const int64_t mid = lo + (hi - lo + 1) / 2;
+                if (tile_end(mid) <= r0 + cap) lo = mid; else hi = mid - 1;
+            }
+            r1 = tile_end(lo);
+        }
+        chunks->emplace_back(r0, r1);
+        r0 = r1;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -285,6 +316,7 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (const char *e = std::getenv("PPB_STREAM_STORES")) p.stream_stores = atoi(e);
     if (const char *e = std::getenv("PPB_A_POLICY")) p.a_policy = atoi(e);
     if (const char *e = std::getenv("PPB_B_POLICY")) p.b_policy = atoi(e);
+    if (const char *e = std::getenv("PPB_STAGGER")) p.stagger_cycles = atoi(e);
     if (const char *e = std::getenv("PPB_DEBUG_SKIP_EPILOGUE")) p.debug_skip_epilogue = atoi(e);
 
     TileKey key{dev, p.nA, p.nB, self, tj, 0, 0, band};
@@ -565,7 +597,8 @@ struct Workspace {
     }
 };
 Workspace g_ws;
-enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_OUT0, WS_OUT1, WS_LAB0, WS_LAB1 };
+constexpr size_t kHostRing = 8;  // result buffers of the host-buffer path (chunks in flight between kernel and D2H)
+enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
 
 struct Stream {
     cudaStream_t s = nullptr;
@@ -641,51 +674,104 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     if (int rc = ws(WS_DEG, 8, &d_deg)) return rc;
     PPB_CUDA(cudaMemsetAsync(d_deg, 0, 8, s_compute.s));
 
-    // row chunks, double-buffered: kernel(c) on s_compute overlaps D2H(c-1) on s_copy
+    // Row chunks: kernel(c) on s_compute overlaps D2H(c-1, c-2, ...) on s_copy.  Chunks end on row-TILE
+    // boundaries (kTI genomes of the row side), so no tile is computed by two launches, and they rotate through
+    // a ring of up to kHostRing device buffers: the result leaves over PCIe at about the rate the kernel
+    // produces it (8 B/pair), so the ring — not a double buffer — is what absorbs the jitter between the two.
     const int rb = out_row_bytes(out_mode, K);
-    const int64_t rows = row_end - row_begin;
+    const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
     size_t free_b = 0, total_b = 0;
     PPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    int64_t chunk = std::min<int64_t>(rows, (int64_t)1 << 27);  // 128 Mi rows = 1 GiB of float2 per buffer
-    const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
-    while (chunk > 1024 && (size_t)(2 * chunk * per_row) > free_b / 2) chunk >>= 1;
-    void *d_out[2] = {nullptr, nullptr}, *d_lab[2] = {nullptr, nullptr};
-    Event done_compute[2], done_copy[2];
-    for (int b = 0; b < 2; b++) {
+    int64_t cap = (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per buffer
+    if (const char *e = std::getenv("PPB_HOST_CHUNK_ROWS")) cap = std::max<int64_t>(1024, atoll(e));
+    while (cap > 1024 && (size_t)(2 * cap * per_row) > free_b / 2) cap >>= 1;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    plan_chunks(n_ref, n_qry, self, row_begin, row_end, cap, &chunks);
+    int64_t max_chunk = 0;
+    for (auto &c : chunks) max_chunk = std::max(max_chunk, c.second - c.first);
+    int n_buf = (int)std::min<size_t>(chunks.size(), kHostRing);
+    while (n_buf > 2 && (size_t)n_buf * max_chunk * per_row > free_b / 2) n_buf--;
+    if (const char *e = std::getenv("PPB_HOST_RING")) n_buf = std::max(1, std::min(atoi(e), (int)kHostRing));
+    n_buf = std::max(1, std::min<int>(n_buf, (int)chunks.size()));
+    const bool trace = std::getenv("PPB_HOST_TRACE") != nullptr;
+
+    void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {};
+    Event done_compute[kHostRing], done_copy[kHostRing];
+    for (int b = 0; b < n_buf; b++) {
         if (out)
-            if (int rc = ws(WS_OUT0 + b, (size_t)chunk * rb, &d_out[b])) return rc;
+            if (int rc = ws(WS_OUT0 + b, (size_t)max_chunk * rb, &d_out[b])) return rc;
         if (labels)
-            if (int rc = ws(WS_LAB0 + b, (size_t)chunk, &d_lab[b])) return rc;
+            if (int rc = ws(WS_LAB0 + b, (size_t)max_chunk, &d_lab[b])) return rc;
         PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
         PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
     }
-    int64_t c = 0;
-    for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk, c++) {
-        const int b = (int)(c & 1);
-        const int64_t r1 = std::min(row_end, r0 + chunk);
-        if (c >= 2) PPB_CUDA(cudaStreamWaitEvent(s_compute.s, done_copy[b].e, 0));  // buffer b drained
+    std::vector<cudaEvent_t> tr;  // PPB_HOST_TRACE: (kernel begin, kernel end, copy begin, copy end) per chunk
+    cudaEvent_t tr_start = nullptr;
+    if (trace) {
+        tr.resize(chunks.size() * 4);
+        for (auto &e : tr) PPB_CUDA(cudaEventCreate(&e));
+        PPB_CUDA(cudaEventCreate(&tr_start));
+        PPB_CUDA(cudaEventRecord(tr_start, s_compute.s));
+    }
+    for (size_t c = 0; c < chunks.size(); c++) {
+        const int b = (int)(c % n_buf);
+        const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
+        if (c >= (size_t)n_buf) PPB_CUDA(cudaStreamWaitEvent(s_compute.s, done_copy[b].e, 0));  // buffer b drained
+        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c], s_compute.s));
         if (int rc = ppb_query_dev((const uint32_t *)d_ref, n_ref, self ? nullptr : (const uint32_t *)d_qry, n_qry,
                                    kmers, K, sketchsize64, (const float *)d_tab, n_clusters,
                                    (const uint16_t *)d_rc, (const uint16_t *)d_qc, r0, r1, out_mode,
                                    out ? d_out[b] : nullptr, boundary, labels ? (int8_t *)d_lab[b] : nullptr,
                                    (unsigned long long *)d_deg, s_compute.s))
             return rc;
+        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 1], s_compute.s));
         PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
         PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
+        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 2], s_copy.s));
         if (out)
             PPB_CUDA(cudaMemcpyAsync((char *)out + (size_t)(r0 - row_begin) * rb, d_out[b], (size_t)(r1 - r0) * rb,
                                      cudaMemcpyDeviceToHost, s_copy.s));
         if (labels)
             PPB_CUDA(cudaMemcpyAsync(labels + (r0 - row_begin), d_lab[b], (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
                                      s_copy.s));
+        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 3], s_copy.s));
         PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
     }
     unsigned long long deg = 0;
     PPB_CUDA(cudaMemcpyAsync(&deg, d_deg, 8, cudaMemcpyDeviceToHost, s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_copy.s));
+    if (trace) {  // one line per chunk on stderr: when its kernel and its copy ran, relative to the first launch
+        double k_sum = 0, c_sum = 0;
+        for (size_t c = 0; c < chunks.size(); c++) {
+            float t[4];
+            for (int e = 0; e < 4; e++) cudaEventElapsedTime(&t[e], tr_start, tr[4 * c + e]);
+            k_sum += t[1] - t[0];
+            c_sum += t[3] - t[2];
+            std::fprintf(stderr, "[ppb_query_host] chunk %3zu rows %lld  kernel %8.2f..%8.2f ms  copy %8.2f..%8.2f ms\n", c,
+                         (long long)(chunks[c].second - chunks[c].first), t[0], t[1], t[2], t[3]);
+        }
+        std::fprintf(stderr, "[ppb_query_host] %zu chunks, ring of %d: kernels %.1f ms, copies %.1f ms\n", chunks.size(),
+                     n_buf, k_sum, c_sum);
+        for (auto &e : tr) cudaEventDestroy(e);
+        cudaEventDestroy(tr_start);
+    }
     if (n_degenerate) *n_degenerate = (int64_t)deg;
     return PPB_OK;
+}
+
+int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,
+                             int64_t cap_rows, int64_t *bounds, int64_t max_chunks) {
+    const int64_t total_rows = ppb_num_rows(n_ref, n_qry, self);
+    if (n_ref < 0 || (!self && n_qry < 0) || row_begin < 0 || row_end > total_rows || row_begin > row_end || cap_rows < 1)
+        return -1;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    plan_chunks(n_ref, n_qry, self, row_begin, row_end, cap_rows, &chunks);
+    for (size_t c = 0; c < chunks.size() && (int64_t)c < max_chunks && bounds; c++) {
+        bounds[2 * c] = chunks[c].first;
+        bounds[2 * c + 1] = chunks[c].second;
+    }
+    return (int64_t)chunks.size();
 }
 
 int ppb_release_workspace(void) {

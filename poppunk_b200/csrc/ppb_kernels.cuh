@@ -92,6 +92,7 @@ struct QueryParams {
     long long edge_cap;
     unsigned long long *edge_count;
     int32_t debug_skip_epilogue;  // measurement only (PPB_DEBUG_SKIP_EPILOGUE): epilogue warps do no work
+    int32_t stagger_cycles;       // >0: compute warps 4-7 start this many cycles late (see query_kernel)
     int32_t a_policy, b_policy;  // L2 eviction priority of row-genome loads / column-genome TMA (0 normal, 1 last, 2 first)
     int8_t *labels;
     int32_t has_boundary;
@@ -545,6 +546,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
+    // Two compute warps share a scheduler (w and w+4).  Started together they reach every k boundary together and
+    // the ALU pipe idles while both reload their 112 row-genome registers from L2; started a few pipeline stages
+    // apart (the ring allows kStages), one of them always has LOP3s to issue while the other reloads.
+    if (p.stagger_cycles > 0 && warp >= 4) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger_cycles) {}
+    }
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, lt++) {
         const int2 tc = p.tiles[tile];
         const int64_t i0 = (int64_t)tc.x * kTI;

@@ -97,6 +97,41 @@ def test_shard_rows():
     assert num_rows(50_000, 1_000_000) == 50_000_000_000
 
 
+def _plan(lib, n_ref, n_qry, self_mode, b, e, cap):
+    n = lib.ppb_plan_host_chunks(n_ref, n_qry, int(self_mode), b, e, cap, None, 0)
+    assert n >= 0
+    bounds = np.zeros((max(n, 1), 2), dtype=np.int64)
+    assert lib.ppb_plan_host_chunks(n_ref, n_qry, int(self_mode), b, e, cap, bounds.ctypes.data, n) == n
+    return bounds[:n]
+
+
+@pytest.mark.parametrize("n_ref,n_qry,self_mode,cap", [(1000, 0, True, 50_000), (1000, 0, True, 700),
+                                                       (130, 0, True, 1 << 26), (300, 517, False, 40_000),
+                                                       (300, 517, False, 100), (65, 0, True, 64), (2, 0, True, 5)])
+def test_host_chunks_cover_rows_and_end_on_row_tiles(lib, n_ref, n_qry, self_mode, cap):
+    """ppb_query_host's launch plan: contiguous cover of the shard, <= cap rows each, and every interior cut is
+    the first row of a genome that starts a 64-genome row tile whenever such a cut fits under the cap."""
+    total = lib.ppb_num_rows(n_ref, n_qry, int(self_mode))
+    for b, e in [(0, total), (total // 3, total - total // 5), (7, 8)]:
+        if e > total or b >= e:
+            continue
+        ch = _plan(lib, n_ref, n_qry, self_mode, b, e, cap)
+        assert ch[0, 0] == b and ch[-1, 1] == e
+        assert (ch[1:, 0] == ch[:-1, 1]).all() and ((ch[:, 1] - ch[:, 0]) > 0).all()
+        assert ((ch[:, 1] - ch[:, 0]) <= cap).all()
+        n_side = n_ref if self_mode else n_qry
+        tile_starts = set()
+        for g in range(0, n_side, 64):
+            if self_mode:
+                tile_starts.add(total if g >= n_ref - 1 else lib.ppb_square_to_condensed(g, g + 1, n_ref))
+            else:
+                tile_starts.add(g * n_ref)
+        rows_per_tile = 64 * n_ref
+        for r0, r1 in ch[:-1]:
+            assert int(r1) in tile_starts or cap < rows_per_tile
+    assert lib.ppb_plan_host_chunks(10, 0, 1, 0, 46, 10, None, 0) == -1   # row_end beyond the triangle
+
+
 def test_dropin_error_conventions(tmp_path, lib):
     """PopPUNK/sketchlib.py:523-524 (RuntimeError) and :575-580 (message + sys.exit(1))."""
     from poppunk_b200 import sketchlib
