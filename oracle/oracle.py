@@ -72,6 +72,21 @@ def lib(native: bool = False):
     L.ppo_long_to_square_multi.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, vp]
     L.ppo_regress_rows.argtypes = [vp, i64, vp, i32, C.c_double, vp]
     L.ppo_regress_rows.restype = i64
+    f32 = C.c_float
+    L.ppo_generate_all_tuples.argtypes = [i64, i64, i32, i64, vp, vp]
+    L.ppo_generate_all_tuples.restype = i64
+    L.ppo_iterate_1d_boundary.argtypes = [C.c_double, i32, f32, f32, f32, f32, vp, vp]
+    L.ppo_iterate_1d_boundary.restype = None
+    L.ppo_threshold_iterate_1d.argtypes = [vp, i64, vp, i64, i32, f32, f32, f32, f32, vp, vp, vp]
+    L.ppo_threshold_iterate_1d.restype = i64
+    L.ppo_threshold_iterate_2d.argtypes = [vp, i64, vp, i64, f32, vp, vp, vp]
+    L.ppo_threshold_iterate_2d.restype = i64
+    L.ppo_get_knn_distances.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+    L.ppo_get_knn_distances.restype = None
+    L.ppo_lower_rank.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, f32, vp, vp, vp]
+    L.ppo_lower_rank.restype = i64
+    L.ppo_extend.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp]
+    L.ppo_extend.restype = i64
     if not native:
         _lib = L
     return L
@@ -181,6 +196,78 @@ def generate_tuples(assignments, within_label, self=True, num_ref=0, int_offset=
     oi, oj = np.empty(a.shape[0], dtype=np.int64), np.empty(a.shape[0], dtype=np.int64)
     n = lib().ppo_generate_tuples(_ptr(a), a.shape[0], within_label, int(self), max(num_ref, 1), int_offset, _ptr(oi), _ptr(oj))
     return oi[:n], oj[:n]
+
+
+def generate_all_tuples(num_ref, num_queries=0, self=True, int_offset=0):
+    """src/boundary.cpp:125-149."""
+    n = num_ref * (num_ref - 1) // 2 if self else num_ref * num_queries
+    oi, oj = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    c = lib().ppo_generate_all_tuples(num_ref, num_queries, int(self), int_offset, _ptr(oi), _ptr(oj))
+    return oi[:c], oj[:c]
+
+
+def iterate_1d_boundary(offset, slope, x0, y0, x1, y1):
+    """(x_max, y_max) of one step of threshold_iterate_1D (src/boundary.cpp:171-185)."""
+    xm, ym = C.c_float(0), C.c_float(0)
+    lib().ppo_iterate_1d_boundary(float(offset), slope, x0, y0, x1, y1, C.byref(xm), C.byref(ym))
+    return xm.value, ym.value
+
+
+def threshold_iterate_1d(dists, offsets, slope, x0, y0, x1, y1):
+    """src/boundary.cpp:151-209: (i, j, offset_idx) int64 arrays."""
+    d = np.ascontiguousarray(dists, dtype=np.float32)
+    off = np.ascontiguousarray(offsets, dtype=np.float64)
+    n = d.shape[0]
+    oi, oj, oo = (np.empty(n, dtype=np.int64) for _ in range(3))
+    c = lib().ppo_threshold_iterate_1d(_ptr(d), n, _ptr(off), off.shape[0], slope, x0, y0, x1, y1, _ptr(oi), _ptr(oj), _ptr(oo))
+    return oi[:c], oj[:c], oo[:c]
+
+
+def threshold_iterate_2d(dists, x_max, y_max):
+    """src/boundary.cpp:211-237: (i, j, offset_idx) int64 arrays."""
+    d = np.ascontiguousarray(dists, dtype=np.float32)
+    xm = np.ascontiguousarray(x_max, dtype=np.float32)
+    cap = d.shape[0] * max(1, xm.shape[0])
+    oi, oj, oo = (np.empty(cap, dtype=np.int64) for _ in range(3))
+    c = lib().ppo_threshold_iterate_2d(_ptr(d), d.shape[0], _ptr(xm), xm.shape[0], y_max, _ptr(oi), _ptr(oj), _ptr(oo))
+    return oi[:c], oj[:c], oo[:c]
+
+
+def get_knn_distances(mat, knn):
+    """src/extend.cpp:245-289: (i, j, dist) of length rows*kNN."""
+    m = np.ascontiguousarray(mat, dtype=np.float32)
+    rows, cols = m.shape
+    oi, oj = np.empty(rows * knn, dtype=np.int64), np.empty(rows * knn, dtype=np.int64)
+    od = np.empty(rows * knn, dtype=np.float32)
+    lib().ppo_get_knn_distances(_ptr(m), rows, cols, knn, _ptr(oi), _ptr(oj), _ptr(od))
+    return oi, oj, od
+
+
+def _coo(i, j, d):
+    return (np.ascontiguousarray(i, dtype=np.int64), np.ascontiguousarray(j, dtype=np.int64),
+            np.ascontiguousarray(d, dtype=np.float32))
+
+
+def lower_rank(i, j, d, n_samples, knn, reciprocal_only=False, count_unique_distances=False, epsilon=0.0):
+    """src/extend.cpp:146-243."""
+    i, j, d = _coo(i, j, d)
+    nnz = i.shape[0]
+    oi, oj, od = np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.float32)
+    c = lib().ppo_lower_rank(_ptr(i), _ptr(j), _ptr(d), nnz, n_samples, knn, int(reciprocal_only),
+                             int(count_unique_distances), epsilon, _ptr(oi), _ptr(oj), _ptr(od))
+    return oi[:c], oj[:c], od[:c]
+
+
+def extend(i, j, d, qq, qr, knn):
+    """src/extend.cpp:52-136; qr is (n_ref, n_query), qq (n_query, n_query)."""
+    i, j, d = _coo(i, j, d)
+    qq = np.ascontiguousarray(qq, dtype=np.float32)
+    qr = np.ascontiguousarray(qr, dtype=np.float32)
+    nr, nq = qr.shape
+    cap = (nr + nq) * knn
+    oi, oj, od = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.float32)
+    c = lib().ppo_extend(_ptr(i), _ptr(j), _ptr(d), i.shape[0], _ptr(qq), _ptr(qr), nr, nq, knn, _ptr(oi), _ptr(oj), _ptr(od))
+    return oi[:c], oj[:c], od[:c]
 
 
 def long_to_square(vec, n):
@@ -304,3 +391,127 @@ def assign_threshold_numpy(dists, slope, x_max, y_max):
     else:
         s = y0 - ym
     return np.sign(s).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own poppunk_refine sources built here (Makefile target `ref`)
+# --------------------------------------------------------------------------------------------
+REF_LIB = os.path.join(_HERE, "_ref", "libpprefine_ref.so")
+_ref = None
+
+
+def build_ref() -> str:
+    """Compile /root/reference/src/{boundary,extend}.cpp (unchanged) into oracle/_ref — needs the reference tree."""
+    subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+    return REF_LIB
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref/libpprefine_ref.so (prebuilt; travels to the GPU box)."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_LIB)
+        i64, vp, f32, ci = C.c_int64, C.c_void_p, C.c_float, C.c_int
+        L.ppr_assign_threshold.argtypes = [vp, i64, ci, f32, f32, ci, vp]
+        L.ppr_assign_threshold.restype = None
+        L.ppr_edge_iterate.argtypes = [vp, i64, ci, f32, f32, vp, vp, i64]
+        L.ppr_generate_tuples.argtypes = [vp, i64, ci, ci, ci, ci, vp, vp, i64]
+        L.ppr_generate_all_tuples.argtypes = [ci, ci, ci, ci, vp, vp, i64]
+        L.ppr_threshold_iterate_1d.argtypes = [vp, i64, vp, i64, ci, f32, f32, f32, f32, ci, vp, vp, vp, i64]
+        L.ppr_threshold_iterate_2d.argtypes = [vp, i64, vp, i64, f32, vp, vp, vp, i64]
+        L.ppr_get_knn_distances.argtypes = [vp, i64, i64, ci, i64, ci, vp, vp, vp, i64]
+        L.ppr_lower_rank.argtypes = [vp, vp, vp, i64, i64, i64, ci, ci, f32, ci, vp, vp, vp, i64]
+        L.ppr_extend.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, i64, ci, vp, vp, vp, i64]
+        for name in ("ppr_edge_iterate", "ppr_generate_tuples", "ppr_generate_all_tuples", "ppr_threshold_iterate_1d",
+                     "ppr_threshold_iterate_2d", "ppr_get_knn_distances", "ppr_lower_rank", "ppr_extend"):
+            getattr(L, name).restype = i64
+        _ref = L
+    return _ref
+
+
+class ref:
+    """The reference functions themselves (same argument meaning as the oracle functions above)."""
+
+    @staticmethod
+    def assign_threshold(dists, slope, x_max, y_max, threads=1):
+        d = np.ascontiguousarray(dists, dtype=np.float32)
+        out = np.empty(d.shape[0], dtype=np.float32)
+        ref_lib().ppr_assign_threshold(_ptr(d), d.shape[0], slope, x_max, y_max, threads, _ptr(out))
+        return out
+
+    @staticmethod
+    def edge_iterate(dists, slope, x_max, y_max):
+        d = np.ascontiguousarray(dists, dtype=np.float32)
+        n = d.shape[0]
+        oi, oj = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        c = ref_lib().ppr_edge_iterate(_ptr(d), n, slope, x_max, y_max, _ptr(oi), _ptr(oj), n)
+        return oi[:c], oj[:c]
+
+    @staticmethod
+    def generate_tuples(assignments, within_label, self=True, num_ref=0, int_offset=0):
+        a = np.ascontiguousarray(assignments, dtype=np.int32)
+        n = a.shape[0]
+        oi, oj = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        c = ref_lib().ppr_generate_tuples(_ptr(a), n, within_label, int(self), max(num_ref, 1), int_offset, _ptr(oi), _ptr(oj), n)
+        return oi[:c], oj[:c]
+
+    @staticmethod
+    def generate_all_tuples(num_ref, num_queries=0, self=True, int_offset=0):
+        n = num_ref * (num_ref - 1) // 2 if self else num_ref * num_queries
+        oi, oj = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        c = ref_lib().ppr_generate_all_tuples(num_ref, num_queries, int(self), int_offset, _ptr(oi), _ptr(oj), n)
+        return oi[:c], oj[:c]
+
+    @staticmethod
+    def threshold_iterate_1d(dists, offsets, slope, x0, y0, x1, y1):
+        d = np.ascontiguousarray(dists, dtype=np.float32)
+        off = np.ascontiguousarray(offsets, dtype=np.float64)
+        n = d.shape[0]
+        oi, oj, oo = (np.empty(n, dtype=np.int64) for _ in range(3))
+        c = ref_lib().ppr_threshold_iterate_1d(_ptr(d), n, _ptr(off), off.shape[0], slope, x0, y0, x1, y1, 1,
+                                               _ptr(oi), _ptr(oj), _ptr(oo), n)
+        return oi[:c], oj[:c], oo[:c]
+
+    @staticmethod
+    def threshold_iterate_2d(dists, x_max, y_max):
+        d = np.ascontiguousarray(dists, dtype=np.float32)
+        xm = np.ascontiguousarray(x_max, dtype=np.float32)
+        cap = d.shape[0] * max(1, xm.shape[0])
+        oi, oj, oo = (np.empty(cap, dtype=np.int64) for _ in range(3))
+        c = ref_lib().ppr_threshold_iterate_2d(_ptr(d), d.shape[0], _ptr(xm), xm.shape[0], y_max, _ptr(oi), _ptr(oj),
+                                               _ptr(oo), cap)
+        return oi[:c], oj[:c], oo[:c]
+
+    @staticmethod
+    def get_knn_distances(mat, knn):
+        m = np.ascontiguousarray(mat, dtype=np.float32)
+        rows, cols = m.shape
+        cap = rows * knn
+        oi, oj, od = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.float32)
+        ref_lib().ppr_get_knn_distances(_ptr(m), rows, cols, knn, 0, 1, _ptr(oi), _ptr(oj), _ptr(od), cap)
+        return oi, oj, od
+
+    @staticmethod
+    def lower_rank(i, j, d, n_samples, knn, reciprocal_only=False, count_unique_distances=False, epsilon=0.0):
+        i, j, d = _coo(i, j, d)
+        nnz = i.shape[0]
+        oi, oj, od = np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.float32)
+        c = ref_lib().ppr_lower_rank(_ptr(i), _ptr(j), _ptr(d), nnz, n_samples, knn, int(reciprocal_only),
+                                     int(count_unique_distances), epsilon, 1, _ptr(oi), _ptr(oj), _ptr(od), nnz)
+        return oi[:c], oj[:c], od[:c]
+
+    @staticmethod
+    def extend(i, j, d, qq, qr, knn):
+        i, j, d = _coo(i, j, d)
+        qq = np.ascontiguousarray(qq, dtype=np.float32)
+        qr = np.ascontiguousarray(qr, dtype=np.float32)
+        nr, nq = qr.shape
+        cap = (nr + nq) * knn
+        oi, oj, od = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.float32)
+        c = ref_lib().ppr_extend(_ptr(i), _ptr(j), _ptr(d), i.shape[0], _ptr(qq), _ptr(qr), nr, nq, knn, 1,
+                                 _ptr(oi), _ptr(oj), _ptr(od), cap)
+        return oi[:c], oj[:c], od[:c]

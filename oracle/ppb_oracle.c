@@ -401,3 +401,291 @@ void ppo_long_to_square_multi(const float *rr, int64_t s_rr, const float *qr, in
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * More of N1 and N3.  The sources of these ARE in the reference tree (src/boundary.cpp,
+ * src/extend.cpp) and build here into oracle/_ref/libpprefine_ref.so (Makefile target `ref`); tests/ checks
+ * every function below against that build, so these restatements are PINNED by the reference itself.
+ * ---------------------------------------------------------------------------------------- */
+
+/* index order of a stable ascending sort of v (boundary.hpp:27-42 sort_indexes): ties keep index order */
+typedef struct {
+    float v;
+    int64_t idx;
+} ppo_keyed;
+static int ppo_keyed_cmp(const void *a, const void *b) {
+    const ppo_keyed *x = (const ppo_keyed *)a, *y = (const ppo_keyed *)b;
+    if (x->v < y->v) return -1;
+    if (y->v < x->v) return 1;
+    return (x->idx > y->idx) - (x->idx < y->idx);
+}
+static void ppo_sort_indexes(const float *v, int64_t stride, int64_t n, ppo_keyed *scratch) {
+    for (int64_t t = 0; t < n; t++) {
+        scratch[t].v = v[t * stride];
+        scratch[t].idx = t;
+    }
+    qsort(scratch, (size_t)n, sizeof(ppo_keyed), ppo_keyed_cmp);
+}
+
+/* N1: src/boundary.cpp:125-149 generate_all_tuples. Returns count. */
+int64_t ppo_generate_all_tuples(int64_t num_ref, int64_t num_queries, int32_t self, int64_t int_offset, int64_t *out_i,
+                                int64_t *out_j) {
+    int64_t cnt = 0;
+    if (self) {
+        const double w = 2.0 * (double)num_ref - 1.0;
+        const int64_t n_rows = (int64_t)((w * w - 1.0) / 8.0); /* (pow(2n-1, 2) - 1) / 8 == n(n-1)/2 */
+        for (int64_t row = 0; row < n_rows; row++, cnt++) {
+            int64_t i = ppo_calc_row_idx(row, num_ref);
+            int64_t j = ppo_calc_col_idx(row, i, num_ref) + int_offset;
+            i += int_offset;
+            out_i[cnt] = i < j ? i : j;
+            out_j[cnt] = i < j ? j : i;
+        }
+    } else {
+        for (int64_t j = 0; j < num_ref; j++)
+            for (int64_t i = 0; i < num_queries; i++, cnt++) {
+                out_i[cnt] = i; /* int_offset is not applied on this branch (:143-147) */
+                out_j[cnt] = j + num_ref;
+            }
+    }
+    return cnt;
+}
+
+/* The boundary of one step of threshold_iterate_1D (src/boundary.cpp:171-185): the point `offset` along the line
+ * (x0,y0)->(x1,y1), turned into axis intercepts.  offsets are double, everything else float: the products are
+ * formed in double and narrowed on assignment, exactly as the mixed-type expressions of the reference do. */
+void ppo_iterate_1d_boundary(double offset, int32_t slope, float x0, float y0, float x1, float y1, float *x_max,
+                             float *y_max) {
+    const float dx = x1 - x0, dy = y1 - y0;
+    const float ds = sqrtf(dx * dx + dy * dy);
+    const float gradient = dy / dx;
+    const float xi = (float)((double)x0 + offset * (double)(dx / ds));
+    const float yi = (float)((double)y0 + offset * (double)(dy / ds));
+    if (slope == 2) {
+        *x_max = xi + yi * gradient;
+        *y_max = yi + xi / gradient;
+    } else if (slope == 0) {
+        *x_max = xi;
+        *y_max = 0;
+    } else {
+        *x_max = 0;
+        *y_max = yi;
+    }
+}
+
+/* N1: src/boundary.cpp:151-209 threshold_iterate_1D.  Rows are ranked once by their signed distance to the FIRST
+ * boundary; each later (sorted) offset then admits rows in that fixed order while line_dist <= 0.  Outputs
+ * (i, j, index of the offset that admitted the row).  Returns count. */
+int64_t ppo_threshold_iterate_1d(const float *dists, int64_t n_rows, const double *offsets, int64_t n_off, int32_t slope,
+                                 float x0, float y0, float x1, float y1, int64_t *out_i, int64_t *out_j,
+                                 int64_t *out_off) {
+    if (n_rows == 0 || n_off == 0) return 0;
+    const int64_t n_samples = (int64_t)(0.5 * (1 + sqrt(1 + 8.0 * (double)n_rows)));
+    ppo_keyed *order = (ppo_keyed *)malloc(sizeof(ppo_keyed) * (size_t)n_rows);
+    float *first = (float *)malloc(sizeof(float) * (size_t)n_rows);
+    int64_t cnt = 0, pos = 0;
+    for (int64_t o = 0; o < n_off; o++) {
+        float x_max, y_max;
+        ppo_iterate_1d_boundary(offsets[o], slope, x0, y0, x1, y1, &x_max, &y_max);
+        if (o == 0) {
+            for (int64_t r = 0; r < n_rows; r++) first[r] = ppo_line_dist(dists[2 * r], dists[2 * r + 1], x_max, y_max, slope);
+            ppo_sort_indexes(first, 1, n_rows, order);
+        }
+        while (pos < n_rows) {
+            const int64_t r = order[pos].idx;
+            if (!(ppo_line_dist(dists[2 * r], dists[2 * r + 1], x_max, y_max, slope) <= 0)) break;
+            const int64_t i = ppo_calc_row_idx(r, n_samples);
+            out_i[cnt] = i;
+            out_j[cnt] = ppo_calc_col_idx(r, i, n_samples);
+            out_off[cnt] = o;
+            cnt++;
+            pos++;
+        }
+    }
+    free(order);
+    free(first);
+    return cnt;
+}
+
+/* N1: src/boundary.cpp:211-237 threshold_iterate_2D: step o admits, in row order, the rows inside the sloped
+ * boundary (x_max[o], y_max) that were outside the previous one.  Returns count. */
+int64_t ppo_threshold_iterate_2d(const float *dists, int64_t n_rows, const float *x_max, int64_t n_off, float y_max,
+                                 int64_t *out_i, int64_t *out_j, int64_t *out_off) {
+    const int64_t n_samples = (int64_t)(0.5 * (1 + sqrt(1 + 8.0 * (double)n_rows)));
+    int64_t cnt = 0;
+    for (int64_t o = 0; o < n_off; o++)
+        for (int64_t r = 0; r < n_rows; r++) {
+            const float x = dists[2 * r], y = dists[2 * r + 1];
+            if (ppo_line_dist(x, y, x_max[o], y_max, 2) <= 0 && (o == 0 || ppo_line_dist(x, y, x_max[o - 1], y_max, 2) > 0)) {
+                const int64_t i = ppo_calc_row_idx(r, n_samples);
+                out_i[cnt] = i;
+                out_j[cnt] = ppo_calc_col_idx(r, i, n_samples);
+                out_off[cnt] = o;
+                cnt++;
+            }
+        }
+    return cnt;
+}
+
+/* N3: src/extend.cpp:245-289 get_kNN_distances.  Row r of a dense rows x cols matrix -> its kNN smallest entries
+ * (ties: lower column first), never column r itself.  Outputs are rows*kNN long, zero where a row has fewer
+ * than kNN candidates (the reference's vectors are value-initialised). */
+void ppo_get_knn_distances(const float *mat, int64_t rows, int64_t cols, int64_t knn, int64_t *out_i, int64_t *out_j,
+                           float *out_d) {
+#pragma omp parallel
+    {
+        ppo_keyed *order = (ppo_keyed *)malloc(sizeof(ppo_keyed) * (size_t)(cols > 0 ? cols : 1));
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < rows; r++) {
+            ppo_sort_indexes(mat + r * cols, 1, cols, order);
+            int64_t k = 0;
+            for (int64_t t = 0; t < knn; t++) {
+                out_i[r * knn + t] = r;
+                out_j[r * knn + t] = 0;
+                out_d[r * knn + t] = 0.0f;
+            }
+            for (int64_t t = 0; t < cols && k < knn; t++) {
+                if (order[t].idx == r) continue;
+                out_j[r * knn + k] = order[t].idx;
+                out_d[r * knn + k] = order[t].v;
+                k++;
+            }
+        }
+        free(order);
+    }
+}
+
+/* CSR row pointers of a COO list sorted by i (src/extend.cpp:14-38 row_start_indices) */
+static void ppo_row_starts(const int64_t *i_vec, int64_t nnz, int64_t n, int64_t *start) {
+    int64_t p = 0;
+    for (int64_t r = 0; r <= n; r++) {
+        while (p < nnz && i_vec[p] < r) p++;
+        start[r] = p;
+    }
+    start[n] = nnz;
+}
+
+/* N3: src/extend.cpp:146-243 lower_rank.  Per row: neighbours in ascending distance (stable), self links dropped;
+ * keep while fewer than... exactly: plain mode keeps an entry while the number already kept is <= kNN (so kNN+1
+ * entries — the reference's own off-by-one, preserved); unique-distance mode counts a new distance whenever it
+ * differs from the previous counted one by >= epsilon and keeps entries while that count is <= kNN.
+ * reciprocal_only then keeps (i<j) entries whose mirror (j,i) was also kept.  Returns count (outputs sized nnz). */
+int64_t ppo_lower_rank(const int64_t *i_vec, const int64_t *j_vec, const float *d_vec, int64_t nnz, int64_t n,
+                       int64_t knn, int32_t reciprocal_only, int32_t count_unique, float epsilon, int64_t *out_i,
+                       int64_t *out_j, float *out_d) {
+    int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 2));
+    int64_t *kept_start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 2));
+    ppo_keyed *order = (ppo_keyed *)malloc(sizeof(ppo_keyed) * (size_t)(nnz > 0 ? nnz : 1));
+    ppo_row_starts(i_vec, nnz, n, start);
+    int64_t cnt = 0;
+    for (int64_t r = 0; r < n; r++) {
+        kept_start[r] = cnt;
+        const int64_t b = start[r], len = start[r + 1] - start[r];
+        if (len <= 0) continue;
+        ppo_sort_indexes(d_vec + b, 1, len, order);
+        int64_t unique = 0, kept = 0;
+        float prev = 0.0f;
+        for (int64_t t = 0; t < len; t++) {
+            const int64_t j = j_vec[b + order[t].idx];
+            const float d = order[t].v;
+            if (j == r) continue;
+            if (count_unique) {
+                if (fabsf(d - prev) >= epsilon) {
+                    unique++;
+                    prev = d;
+                }
+            } else {
+                unique = kept;
+            }
+            if (unique > knn) break;
+            out_i[cnt] = r;
+            out_j[cnt] = j;
+            out_d[cnt] = d;
+            cnt++;
+            kept++;
+        }
+    }
+    kept_start[n] = cnt;
+    if (reciprocal_only) {
+        int64_t w = 0;
+        int64_t *ti = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt > 0 ? cnt : 1));
+        int64_t *tj = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt > 0 ? cnt : 1));
+        float *td = (float *)malloc(sizeof(float) * (size_t)(cnt > 0 ? cnt : 1));
+        for (int64_t t = 0; t < cnt; t++) {
+            const int64_t i = out_i[t], j = out_j[t];
+            if (!(i < j) || j >= n) continue;
+            int found = 0;
+            for (int64_t u = kept_start[j]; u < kept_start[j + 1] && !found; u++) found = out_j[u] == i;
+            if (found) {
+                ti[w] = i;
+                tj[w] = j;
+                td[w] = out_d[t];
+                w++;
+            }
+        }
+        memcpy(out_i, ti, sizeof(int64_t) * (size_t)w);
+        memcpy(out_j, tj, sizeof(int64_t) * (size_t)w);
+        memcpy(out_d, td, sizeof(float) * (size_t)w);
+        free(ti);
+        free(tj);
+        free(td);
+        cnt = w;
+    }
+    free(start);
+    free(kept_start);
+    free(order);
+    return cnt;
+}
+
+/* N3: src/extend.cpp:52-136 extend.  Sample s < nr is a reference: candidates are its sparse ref-ref row and its
+ * dense row of qr (nr x nq); sample s >= nr is a query: candidates are its column of qr (the refs) and its row of
+ * qq (nq x nq).  Both lists are sorted (stable) and merged, the dense-query list winning ties; j of a query
+ * candidate is nr + its index; self links are skipped; the first kNN survive.  Returns count (outputs sized
+ * (nr+nq)*kNN).  A row that runs out of candidates before kNN simply ends (the reference would raise there). */
+int64_t ppo_extend(const int64_t *i_vec, const int64_t *j_vec, const float *d_vec, int64_t nnz, const float *qq,
+                   const float *qr, int64_t nr, int64_t nq, int64_t knn, int64_t *out_i, int64_t *out_j, float *out_d) {
+    int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nr + 2));
+    const int64_t big = (nnz > nr ? nnz : nr) + nq + 1;
+    ppo_keyed *oq = (ppo_keyed *)malloc(sizeof(ppo_keyed) * (size_t)big);
+    ppo_keyed *orr = (ppo_keyed *)malloc(sizeof(ppo_keyed) * (size_t)big);
+    ppo_row_starts(i_vec, nnz, nr, start);
+    int64_t cnt = 0;
+    for (int64_t s = 0; s < nr + nq; s++) {
+        int64_t n_rr, n_qr = nq;
+        if (s < nr) {
+            n_rr = start[s + 1] - start[s];
+            if (n_rr < 0) n_rr = 0;
+            ppo_sort_indexes(qr + s * nq, 1, nq, oq);
+            ppo_sort_indexes(d_vec + start[s], 1, n_rr, orr);
+        } else {
+            n_rr = nr;
+            ppo_sort_indexes(qq + (s - nr) * nq, 1, nq, oq);
+            ppo_sort_indexes(qr + (s - nr), nq, nr, orr);
+        }
+        int64_t a = 0, b = 0, kept = 0;
+        while (a < n_qr || b < n_rr) {
+            int64_t j;
+            float d;
+            if (b == n_rr || (a < n_qr && oq[a].v <= orr[b].v)) {
+                j = oq[a].idx + nr;
+                d = oq[a].v;
+                a++;
+            } else {
+                j = s < nr ? j_vec[start[s] + orr[b].idx] : orr[b].idx;
+                d = orr[b].v;
+                b++;
+            }
+            if (j == s) continue;
+            if (kept >= knn) break;
+            out_i[cnt] = s;
+            out_j[cnt] = j;
+            out_d[cnt] = d;
+            cnt++;
+            kept++;
+        }
+    }
+    free(start);
+    free(oq);
+    free(orr);
+    return cnt;
+}

@@ -14,6 +14,10 @@ Fixtures written next to this file:
                        lists its ``iter_tuples`` loop (:30-38) derives from them for a seeded 100-sample cloud
   fit_kmer_curve.npz   PopPUNK/sketchlib.py:635-670 ``fitKmerCurve`` (scipy bounded least squares) run on
                        seeded per-k Jaccard vectors: pins model, clamp and (core, acc) output order
+  refine_ref.npz       outputs of the reference's OWN compiled poppunk_refine functions (src/boundary.cpp, src/extend.cpp
+                       built into oracle/_ref by `make -C oracle ref`): assign_threshold, edge_iterate, generate_tuples,
+                       generate_all_tuples, threshold_iterate_1D/2D, get_kNN_distances, lower_rank, extend on seeded
+                       inputs with many tied distances; inputs are stored beside the outputs
 """
 import ast
 import json
@@ -105,7 +109,63 @@ def fit_kmer_curve():
           "clamped acc:", int((ex[:, 1] == 0).sum()))
 
 
+def refine_ref():
+    root = os.path.dirname(os.path.dirname(HERE))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import oracle
+    oracle.build_ref()
+    R = oracle.ref
+    rng = np.random.default_rng(20240)
+    out = {}
+
+    def put(name, arrays):
+        for t, a in enumerate(arrays):
+            out[f"{name}.{t}"] = np.asarray(a)
+
+    n = 60
+    rows = n * (n - 1) // 2
+    d = (rng.random((rows, 2)) * 0.5).astype(np.float32)
+    d[::7] = d[3]            # tied rows
+    d[5] = (0.0, 0.0)
+    out["dists"] = d
+    for slope, xm, ym in [(2, 0.2, 0.3), (0, 0.1, 0.0), (1, 0.0, 0.2), (2, 0.0, 0.3)]:
+        put(f"assign_threshold/{slope}/{xm}/{ym}", [R.assign_threshold(d, slope, xm, ym)])
+        put(f"edge_iterate/{slope}/{xm}/{ym}", R.edge_iterate(d, slope, xm, ym))
+    lab = rng.integers(-1, 2, rows).astype(np.int32)
+    out["labels"] = lab
+    for self_, nr, off in [(1, 0, 0), (1, 0, 5), (0, 12, 0), (0, 12, 3)]:
+        put(f"generate_tuples/{self_}/{nr}/{off}", R.generate_tuples(lab, -1, bool(self_), nr, off))
+    for nr, nq, self_, off in [(17, 0, 1, 0), (17, 0, 1, 4), (5, 7, 0, 0), (5, 7, 0, 3)]:
+        put(f"generate_all_tuples/{nr}/{nq}/{self_}/{off}", R.generate_all_tuples(nr, nq, bool(self_), off))
+    offs = np.linspace(-0.1, 0.5, 23)
+    out["offsets"] = offs
+    for slope in (0, 1, 2):
+        put(f"threshold_iterate_1d/{slope}", R.threshold_iterate_1d(d, offs, slope, 0.05, 0.05, 0.4, 0.45))
+    xmr = (np.sort(rng.random(9)) * 0.6).astype(np.float32)
+    out["x_max_range"] = xmr
+    put("threshold_iterate_2d", R.threshold_iterate_2d(d, xmr, 0.3))
+    sq = np.round(rng.random((40, 40)), 1).astype(np.float32)   # one decimal: many ties
+    rect = np.round(rng.random((7, 30)), 1).astype(np.float32)
+    out["square"], out["rect"] = sq, rect
+    for k in (1, 3, 39):
+        put(f"knn/square/{k}", R.get_knn_distances(sq, k))
+    put("knn/rect/1", R.get_knn_distances(rect, 1))
+    ci, cj, cd = R.get_knn_distances(sq, 10)
+    for rec in (0, 1):
+        for cu in (0, 1):
+            for k in (1, 2, 5):
+                put(f"lower_rank/{rec}/{cu}/{k}", R.lower_rank(ci, cj, cd, 40, k, bool(rec), bool(cu), 0.05))
+    qr = np.round(rng.random((40, 9)), 1).astype(np.float32)
+    qq = np.round(rng.random((9, 9)), 1).astype(np.float32)
+    out["qr"], out["qq"] = qr, qq
+    for k in (1, 3, 8):
+        put(f"extend/{k}", R.extend(ci, cj, cd, qq, qr, k))
+    np.savez_compressed(os.path.join(HERE, "refine_ref.npz"), **out)
+    print("refine_ref:", len(out), "arrays from oracle/_ref/libpprefine_ref.so")
+
+
 if __name__ == "__main__":
+    refine_ref()
     json_sketch()
     refine_grid()
     fit_kmer_curve()
