@@ -167,6 +167,47 @@ int ppb_edges_from_labels_dev(const void *d_labels, int32_t label_dtype, int64_t
                               int64_t *d_i, int64_t *d_j, int64_t capacity, int64_t *d_count,
                               void *d_scratch, void *stream);
 
+/* N1 (rest) — src/boundary.cpp:125-237, bound at src/python_bindings.cpp:42-77.
+ * ppb_generate_all_tuples_dev: generate_all_tuples — every pair of the triangle (self) or rectangle, as (i, j);
+ *   d_i / d_j hold n(n-1)/2 (self) or num_ref*num_queries entries.
+ * ppb_threshold_iterate_1d_dev: threshold_iterate_1D — the boundary moves along the line (x0,y0)->(x1,y1) by the
+ *   (sorted, HOST) offsets; rows are ranked once by their signed distance to the first boundary (stable) and each
+ *   offset admits the next rows of that order with line_dist <= 0.  Outputs (i, j, index of the admitting offset)
+ *   in admission order; *d_count = number admitted (<= n_rows; rows beyond `capacity` are not written).
+ *   Synchronises the stream once (it has to know whether the exact sequential walk is needed).
+ * ppb_threshold_iterate_2d_dev: threshold_iterate_2D — sloped boundaries (x_max[o], y_max), x_max sorted, HOST array
+ *   of at most 1024 entries; step o admits, in row order, the rows inside boundary o and outside boundary o-1.    */
+int ppb_generate_all_tuples_dev(int64_t num_ref, int64_t num_queries, int32_t self, int64_t int_offset,
+                                int64_t *d_i, int64_t *d_j, void *stream);
+int ppb_threshold_iterate_1d_dev(const float *d_dists, int64_t n_rows, const double *offsets, int32_t n_off,
+                                 int32_t slope, float x0, float y0, float x1, float y1,
+                                 int64_t *d_i, int64_t *d_j, int64_t *d_off, int64_t capacity, int64_t *d_count,
+                                 void *stream);
+int ppb_threshold_iterate_2d_dev(const float *d_dists, int64_t n_rows, const float *x_max, int32_t n_off, float y_max,
+                                 int64_t *d_i, int64_t *d_j, int64_t *d_off, int64_t capacity, int64_t *d_count,
+                                 void *stream);
+
+/* N3 — nearest-neighbour extraction for the lineage models (src/extend.cpp:52-289, bound at
+ * src/python_bindings.cpp:109-136; callers PopPUNK/models.py:1177-1184, 1215-1222, 1366-1372, assign.py:680-686,
+ * mandrake.py:67).  Sparse matrices are COO triples (i sorted ascending, as every producer here emits them).
+ * ppb_knn_dev: get_kNN_distances — per row of a dense rows x cols float32 matrix the kNN smallest entries, ties to
+ *   the lower column, never column == row; outputs rows*kNN long (zeros where a row has fewer candidates).
+ * ppb_lower_rank_dev: lower_rank — per sample its sparse neighbours in ascending (stable) order, kept while the
+ *   reference's rank rule holds (plain: kNN+1 entries; count_unique_distances: distances differing by >= epsilon
+ *   count as new ranks), optionally only reciprocal (i<j) pairs.  Outputs sized nnz; *d_count = entries written.
+ *   At most 1024 sparse neighbours per sample.  Synchronises the stream.
+ * ppb_extend_dev: extend — the kNN of every reference (sparse ref-ref row + dense row of qr [nr x nq]) and every
+ *   query (column of qr + row of qq [nq x nq]); the dense query part wins ties; outputs sized (nr+nq)*kNN.
+ * kNN <= 2048.                                                                                                */
+int ppb_knn_dev(const float *d_mat, int64_t rows, int64_t cols, int32_t knn,
+                int64_t *d_i, int64_t *d_j, float *d_d, void *stream);
+int ppb_lower_rank_dev(const int64_t *d_sp_i, const int64_t *d_sp_j, const float *d_sp_d, int64_t nnz,
+                       int64_t n_samples, int64_t knn, int32_t reciprocal_only, int32_t count_unique_distances,
+                       float epsilon, int64_t *d_i, int64_t *d_j, float *d_d, int64_t *d_count, void *stream);
+int ppb_extend_dev(const int64_t *d_sp_i, const int64_t *d_sp_j, const float *d_sp_d, int64_t nnz,
+                   const float *d_qq, const float *d_qr, int64_t nr, int64_t nq, int32_t knn,
+                   int64_t *d_i, int64_t *d_j, float *d_d, int64_t *d_count, void *stream);
+
 /* N2 — long <-> square reshapes (pp_sketchlib.longToSquare / squareToLong / longToSquareMulti; call sites
  * PopPUNK/utils.py:393-405, network.py:2133-2134, models.py:1217,1357, mandrake.py:165).  float32; the
  * condensed / rectangular vectors are read with an element stride so a column of the (n_pairs,2) distance

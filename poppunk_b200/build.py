@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libppb.so")
 SOURCES = ["ppb_api.cu"]
-DEPS = ["ppb_api.cu", "ppb_kernels.cuh", "ppb_ptx.cuh", os.path.join("..", "..", "include", "ppb.h")]
+DEPS = ["ppb_api.cu", "ppb_kernels.cuh", "ppb_ptx.cuh", "ppb_next.cuh", "ppb_refine.cuh", os.path.join("..", "..", "include", "ppb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

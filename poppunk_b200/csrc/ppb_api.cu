@@ -12,8 +12,11 @@
 #include <tuple>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "ppb_kernels.cuh"
 #include "ppb_next.cuh"
+#include "ppb_refine.cuh"
 
 namespace {
 
@@ -522,6 +525,250 @@ int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, flo
         reinterpret_cast<const float2 *>(d_dists), n, slope, x_max, y_max, d_out);
     g_launches++;
     PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N1 (rest) / N3 entry points: threshold iteration, all tuples, kNN / lowerRank / extend
+// ---------------------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+// stream-ordered scratch that frees itself (also on the error paths)
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() {
+        for (void *q : ptrs) cudaFreeAsync(q, st);
+    }
+    template <typename T> int get(T **out, size_t count) {
+        void *q = nullptr;
+        if (cudaMallocAsync(&q, std::max<size_t>(count * sizeof(T), 256), st) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PPB_ERR_NOMEM, "cudaMallocAsync failed for " + std::to_string(count * sizeof(T)) + " bytes");
+        }
+        ptrs.push_back(q);
+        *out = (T *)q;
+        return PPB_OK;
+    }
+};
+// boundary of one step of threshold_iterate_1D (src/boundary.cpp:171-185): offsets are double, the rest float;
+// mixed expressions are evaluated in double and narrowed on assignment, as the reference's are
+void iterate_1d_boundary(double offset, int slope, float x0, float y0, float x1, float y1, float *x_max, float *y_max) {
+    const float dx = x1 - x0, dy = y1 - y0;
+    const float ds = std::sqrt(dx * dx + dy * dy);
+    const float gradient = dy / dx;
+    const float xi = (float)((double)x0 + offset * (double)(dx / ds));
+    const float yi = (float)((double)y0 + offset * (double)(dy / ds));
+    if (slope == 2) {
+        *x_max = xi + yi * gradient;
+        *y_max = yi + xi / gradient;
+    } else if (slope == 0) {
+        *x_max = xi;
+        *y_max = 0;
+    } else {
+        *x_max = 0;
+        *y_max = yi;
+    }
+}
+}  // namespace
+}  // extern "C++"
+
+int ppb_generate_all_tuples_dev(int64_t num_ref, int64_t num_queries, int32_t self, int64_t int_offset, int64_t *d_i,
+                                int64_t *d_j, void *stream) {
+    if (num_ref < 0 || num_queries < 0) return fail(PPB_ERR_ARG, "ppb_generate_all_tuples_dev: bad argument");
+    const int64_t total = self ? num_ref * (num_ref - 1) / 2 : num_ref * num_queries;
+    if (total == 0) return PPB_OK;
+    if (!d_i || !d_j) return fail(PPB_ERR_ARG, "ppb_generate_all_tuples_dev: bad argument");
+    ppb::all_tuples_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(num_ref, num_queries, self,
+                                                                                           int_offset, total, d_i, d_j);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_threshold_iterate_2d_dev(const float *d_dists, int64_t n_rows, const float *x_max, int32_t n_off, float y_max,
+                                 int64_t *d_i, int64_t *d_j, int64_t *d_off, int64_t capacity, int64_t *d_count,
+                                 void *stream) {
+    if (n_rows < 0 || n_off < 0 || (n_rows > 0 && !d_dists) || (n_off > 0 && !x_max) || !d_count || capacity < 0 ||
+        (capacity > 0 && (!d_i || !d_j || !d_off)))
+        return fail(PPB_ERR_ARG, "ppb_threshold_iterate_2d_dev: bad argument");
+    if (n_off > ppb::kIterMaxOffsets) return fail(PPB_ERR_ARG, "ppb_threshold_iterate_2d_dev: at most 1024 offsets per call");
+    for (int o = 1; o < n_off; o++)  // python_bindings.cpp:70-73
+        if (x_max[o] < x_max[o - 1]) return fail(PPB_ERR_ARG, "x_max range to thresholdIterate2D must be sorted");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0 || n_off == 0) {
+        PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+        return PPB_OK;
+    }
+    const int64_t blocks = (n_rows + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+    if (blocks > 0x7fffffff) return fail(PPB_ERR_ARG, "ppb_threshold_iterate_2d_dev: too many rows for one call");
+    Scratch sc(st);
+    float *d_x = nullptr;
+    int64_t *cnt = nullptr;
+    if (int rc = sc.get(&d_x, (size_t)n_off)) return rc;
+    if (int rc = sc.get(&cnt, (size_t)n_off * blocks)) return rc;
+    PPB_CUDA(cudaMemcpyAsync(d_x, x_max, sizeof(float) * n_off, cudaMemcpyHostToDevice, st));
+    const float2 *d2 = reinterpret_cast<const float2 *>(d_dists);
+    ppb::iterate2d_kernel<<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(d2, n_rows, d_x, n_off, y_max, 0, cnt, blocks,
+                                                                         capacity, d_i, d_j, d_off);
+    ppb::scan_kernel<<<1, 1024, 0, st>>>(cnt, (int64_t)n_off * blocks, d_count);
+    ppb::iterate2d_kernel<<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(d2, n_rows, d_x, n_off, y_max, 1, cnt, blocks,
+                                                                         capacity, d_i, d_j, d_off);
+    g_launches += 3;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_threshold_iterate_1d_dev(const float *d_dists, int64_t n_rows, const double *offsets, int32_t n_off, int32_t slope,
+                                 float x0, float y0, float x1, float y1, int64_t *d_i, int64_t *d_j, int64_t *d_off,
+                                 int64_t capacity, int64_t *d_count, void *stream) {
+    if (n_rows < 0 || n_off < 0 || (n_rows > 0 && !d_dists) || (n_off > 0 && !offsets) || !d_count || capacity < 0 ||
+        (capacity > 0 && (!d_i || !d_j || !d_off)) || slope < 0 || slope > 2)
+        return fail(PPB_ERR_ARG, "ppb_threshold_iterate_1d_dev: bad argument");
+    for (int o = 1; o < n_off; o++)  // python_bindings.cpp:56-58
+        if (offsets[o] < offsets[o - 1]) return fail(PPB_ERR_ARG, "Offsets to thresholdIterate1D must be sorted");
+    cudaStream_t st = (cudaStream_t)stream;
+    PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    if (n_rows == 0 || n_off == 0) return PPB_OK;
+    if (n_rows > ((int64_t)1 << 40)) return fail(PPB_ERR_ARG, "ppb_threshold_iterate_1d_dev: too many rows");
+    std::vector<float2> bnd((size_t)n_off);
+    for (int o = 0; o < n_off; o++) iterate_1d_boundary(offsets[o], slope, x0, y0, x1, y1, &bnd[o].x, &bnd[o].y);
+    Scratch sc(st);
+    float2 *d_bnd = nullptr;
+    uint32_t *k_in = nullptr, *k_out = nullptr;
+    int64_t *r_in = nullptr, *order = nullptr;
+    int32_t *first = nullptr, *block_max = nullptr;
+    unsigned long long *counters = nullptr;  // [0] non-monotone rows, [1] rows emitted
+    const int64_t blocks = (n_rows + ppb::kScanBlock - 1) / ppb::kScanBlock;
+    if (int rc = sc.get(&d_bnd, (size_t)n_off)) return rc;
+    if (int rc = sc.get(&k_in, (size_t)n_rows)) return rc;
+    if (int rc = sc.get(&k_out, (size_t)n_rows)) return rc;
+    if (int rc = sc.get(&r_in, (size_t)n_rows)) return rc;
+    if (int rc = sc.get(&order, (size_t)n_rows)) return rc;
+    if (int rc = sc.get(&first, (size_t)n_rows)) return rc;
+    if (int rc = sc.get(&block_max, (size_t)blocks)) return rc;
+    if (int rc = sc.get(&counters, 2)) return rc;
+    PPB_CUDA(cudaMemcpyAsync(d_bnd, bnd.data(), sizeof(float2) * n_off, cudaMemcpyHostToDevice, st));
+    PPB_CUDA(cudaMemsetAsync(counters, 0, 16, st));
+    const float2 *d2 = reinterpret_cast<const float2 *>(d_dists);
+    ppb::iterate1d_keys_kernel<<<grid_for(n_rows, 256, 148 * 16), 256, 0, st>>>(d2, n_rows, slope, bnd[0].x, bnd[0].y, k_in, r_in);
+    // stable LSD radix sort (CUB): equal distances keep row order, like the reference's stable sort
+    size_t temp_bytes = 0;
+    PPB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, k_in, k_out, r_in, order, n_rows, 0, 32, st));
+    uint8_t *temp = nullptr;
+    if (int rc = sc.get(&temp, temp_bytes)) return rc;
+    PPB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, r_in, order, n_rows, 0, 32, st));
+    ppb::iterate1d_first_kernel<<<(unsigned)blocks, ppb::kScanBlock, 0, st>>>(d2, order, n_rows, slope, d_bnd, n_off, first,
+                                                                              block_max, counters);
+    ppb::max_scan_kernel<<<1, 1024, 0, st>>>(block_max, blocks);
+    ppb::iterate1d_emit_kernel<<<(unsigned)blocks, ppb::kScanBlock, 0, st>>>(order, first, block_max, n_rows, n_off, capacity,
+                                                                             d_i, d_j, d_off, counters + 1);
+    g_launches += 5;
+    PPB_CUDA(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    PPB_CUDA(cudaMemcpyAsync(h, counters, 16, cudaMemcpyDeviceToHost, st));
+    PPB_CUDA(cudaStreamSynchronize(st));
+    if (h[0] != 0) {  // a row's test flips back with a later offset (float rounding): redo as the reference's exact walk
+        ppb::iterate1d_sequential_kernel<<<1, 32, 0, st>>>(d2, order, n_rows, slope, d_bnd, n_off, capacity, d_i, d_j, d_off,
+                                                           counters + 1);
+        g_launches++;
+        PPB_CUDA(cudaGetLastError());
+    }
+    PPB_CUDA(cudaMemcpyAsync(d_count, counters + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return PPB_OK;
+}
+
+int ppb_knn_dev(const float *d_mat, int64_t rows, int64_t cols, int32_t knn, int64_t *d_i, int64_t *d_j, float *d_d,
+                void *stream) {
+    if (rows < 0 || cols < 0 || knn < 1 || knn > ppb::kKnnMax || cols > 0xffffffffLL)
+        return fail(PPB_ERR_ARG, "ppb_knn_dev: kNN must be in [1, 2048]");
+    if (rows == 0) return PPB_OK;
+    if (!d_mat || !d_i || !d_j || !d_d) return fail(PPB_ERR_ARG, "ppb_knn_dev: bad argument");
+    int dev = 0, sms = 0;
+    PPB_CUDA(cudaGetDevice(&dev));
+    if (int rc = num_sms(dev, &sms)) return rc;
+    ppb::knn_kernel<ppb::DenseRowCands><<<(unsigned)std::min<int64_t>(rows, (int64_t)sms * 8), ppb::kKnnThreads, 0,
+                                          (cudaStream_t)stream>>>(ppb::DenseRowCands{d_mat, cols}, rows, knn, d_i, d_j, d_d);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_extend_dev(const int64_t *d_sp_i, const int64_t *d_sp_j, const float *d_sp_d, int64_t nnz, const float *d_qq,
+                   const float *d_qr, int64_t nr, int64_t nq, int32_t knn, int64_t *d_i, int64_t *d_j, float *d_d,
+                   int64_t *d_count, void *stream) {
+    if (nnz < 0 || nr < 0 || nq < 0 || knn < 1 || knn > ppb::kKnnMax || !d_count || nr + nq > 0xffffffffLL ||
+        (nnz > 0 && (!d_sp_i || !d_sp_j || !d_sp_d)) || (nq > 0 && !d_qq) || (nr > 0 && nq > 0 && !d_qr))
+        return fail(PPB_ERR_ARG, "ppb_extend_dev: bad argument (kNN must be in [1, 2048])");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_total = nr + nq;
+    if (n_total == 0) {
+        PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+        return PPB_OK;
+    }
+    if (!d_i || !d_j || !d_d) return fail(PPB_ERR_ARG, "ppb_extend_dev: bad argument");
+    Scratch sc(st);
+    int64_t *row_start = nullptr, *cnt = nullptr;
+    if (int rc = sc.get(&row_start, (size_t)nr + 1)) return rc;
+    if (int rc = sc.get(&cnt, (size_t)n_total)) return rc;
+    ppb::row_starts_kernel<<<grid_for(nr + 1, 256, 148 * 8), 256, 0, st>>>(d_sp_i, nnz, nr, row_start);
+    ppb::ExtendCands c{row_start, d_sp_j, d_sp_d, d_qq, d_qr, nr, nq, cnt};
+    ppb::extend_count_kernel<<<grid_for(n_total, 256, 148 * 8), 256, 0, st>>>(c, n_total, knn, cnt);
+    ppb::scan_kernel<<<1, 1024, 0, st>>>(cnt, n_total, d_count);
+    int dev = 0, sms = 0;
+    PPB_CUDA(cudaGetDevice(&dev));
+    if (int rc = num_sms(dev, &sms)) return rc;
+    ppb::knn_kernel<ppb::ExtendCands><<<(unsigned)std::min<int64_t>(n_total, (int64_t)sms * 8), ppb::kKnnThreads, 0, st>>>(
+        c, n_total, knn, d_i, d_j, d_d);
+    g_launches += 4;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
+int ppb_lower_rank_dev(const int64_t *d_sp_i, const int64_t *d_sp_j, const float *d_sp_d, int64_t nnz, int64_t n_samples,
+                       int64_t knn, int32_t reciprocal_only, int32_t count_unique_distances, float epsilon, int64_t *d_i,
+                       int64_t *d_j, float *d_d, int64_t *d_count, void *stream) {
+    if (nnz < 0 || n_samples < 0 || knn < 0 || !d_count || (nnz > 0 && (!d_sp_i || !d_sp_j || !d_sp_d || !d_i || !d_j || !d_d)))
+        return fail(PPB_ERR_ARG, "ppb_lower_rank_dev: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    if (nnz == 0 || n_samples == 0) return PPB_OK;
+    Scratch sc(st);
+    int64_t *row_start = nullptr, *st_j = nullptr, *kept = nullptr, *cnt = nullptr;
+    float *st_d = nullptr;
+    uint8_t *flag = nullptr;
+    int32_t *too_long = nullptr;
+    if (int rc = sc.get(&row_start, (size_t)n_samples + 1)) return rc;
+    if (int rc = sc.get(&st_j, (size_t)nnz)) return rc;
+    if (int rc = sc.get(&st_d, (size_t)nnz)) return rc;
+    if (int rc = sc.get(&kept, (size_t)n_samples)) return rc;
+    if (int rc = sc.get(&cnt, (size_t)n_samples)) return rc;
+    if (int rc = sc.get(&too_long, 1)) return rc;
+    PPB_CUDA(cudaMemsetAsync(too_long, 0, 4, st));
+    ppb::row_starts_kernel<<<grid_for(n_samples + 1, 256, 148 * 8), 256, 0, st>>>(d_sp_i, nnz, n_samples, row_start);
+    const unsigned blocks = (unsigned)((n_samples + ppb::kLowerWarps - 1) / ppb::kLowerWarps);
+    ppb::lower_rank_keep_kernel<<<blocks, ppb::kLowerWarps * 32, 0, st>>>(row_start, d_sp_j, d_sp_d, n_samples, knn,
+                                                                         count_unique_distances, epsilon, st_j, st_d, kept,
+                                                                         too_long);
+    g_launches += 2;
+    if (reciprocal_only) {
+        if (int rc = sc.get(&flag, (size_t)nnz)) return rc;
+        ppb::lower_rank_reciprocal_kernel<<<grid_for(n_samples, 128, 148 * 16), 128, 0, st>>>(row_start, st_j, kept, n_samples,
+                                                                                             flag, cnt);
+        g_launches++;
+    } else {
+        PPB_CUDA(cudaMemcpyAsync(cnt, kept, sizeof(int64_t) * n_samples, cudaMemcpyDeviceToDevice, st));
+    }
+    ppb::scan_kernel<<<1, 1024, 0, st>>>(cnt, n_samples, d_count);
+    ppb::lower_rank_write_kernel<<<grid_for(n_samples, 128, 148 * 16), 128, 0, st>>>(row_start, st_j, st_d, kept, flag, cnt,
+                                                                                    n_samples, d_i, d_j, d_d);
+    g_launches += 2;
+    PPB_CUDA(cudaGetLastError());
+    int32_t h_long = 0;
+    PPB_CUDA(cudaMemcpyAsync(&h_long, too_long, 4, cudaMemcpyDeviceToHost, st));
+    PPB_CUDA(cudaStreamSynchronize(st));
+    if (h_long) return fail(PPB_ERR_ARG, "ppb_lower_rank_dev: a sample has more than 1024 sparse neighbours");
     return PPB_OK;
 }
 
