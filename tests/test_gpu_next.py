@@ -95,3 +95,81 @@ def test_long_square_roundtrip(eng, oracle):
     core = reshape.longToSquare(distVec=d[:, [0]], num_threads=1)
     i, j = np.triu_indices(40, k=1)
     assert (core[i, j] == d[:, 0]).all()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# N1 (rest) and N3: against the golden vectors of the reference's own compiled sources (tests/golden/refine_ref.npz,
+# made from oracle/_ref) and against the oracle restatement on larger seeded inputs
+# ------------------------------------------------------------------------------------------------------------
+def _lists(arrays):
+    return tuple(np.asarray(a).tolist() for a in arrays)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "refine_ref.npz"))
+
+
+def _gold(gold, name, n):
+    return tuple(gold[f"{name}.{t}"].tolist() for t in range(n))
+
+
+def test_refine_rest_matches_reference_golden(eng, gold):
+    from poppunk_b200 import refine
+    d = gold["dists"]
+    for slope in (0, 1, 2):
+        got = refine.thresholdIterate1D(d, gold["offsets"], slope, 0.05, 0.05, 0.4, 0.45)
+        assert got == _gold(gold, f"threshold_iterate_1d/{slope}", 3)
+    assert refine.thresholdIterate2D(d, gold["x_max_range"], 0.3) == _gold(gold, "threshold_iterate_2d", 3)
+    for nr, nq, self_, off in [(17, 0, 1, 0), (17, 0, 1, 4), (5, 7, 0, 0), (5, 7, 0, 3)]:
+        exp = _gold(gold, f"generate_all_tuples/{nr}/{nq}/{self_}/{off}", 2)
+        assert refine.generateAllTuples(nr, nq, bool(self_), off) == list(zip(*exp))
+    for k in (1, 3, 39):
+        assert refine.get_kNN_distances(gold["square"], k) == _gold(gold, f"knn/square/{k}", 3)
+    assert refine.get_kNN_distances(gold["rect"], 1) == _gold(gold, "knn/rect/1", 3)
+    ci, cj, cd = (gold[f"knn/square/39.{t}"].reshape(40, 39)[:, :10].reshape(-1) for t in range(3))
+    for rec in (0, 1):
+        for cu in (0, 1):
+            for k in (1, 2, 5):
+                got = refine.lowerRank((ci, cj, cd), 40, k, bool(rec), bool(cu), 0.05)
+                assert got == _gold(gold, f"lower_rank/{rec}/{cu}/{k}", 3), (rec, cu, k)
+    for k in (1, 3, 8):
+        assert refine.extend((ci, cj, cd), gold["qq"], gold["qr"], k) == _gold(gold, f"extend/{k}", 3)
+
+
+def test_refine_rest_vs_oracle_larger(eng, oracle):
+    """sizes that span many CTAs / scan blocks, distances quantised so that ties are everywhere"""
+    from poppunk_b200 import refine
+    rng = np.random.default_rng(5)
+    n = 700
+    rows = n * (n - 1) // 2                       # 244,650 rows: 60 compaction blocks, 239 scan blocks
+    d = np.round(rng.random((rows, 2)) * 0.6, 3).astype(np.float32)
+    offs = np.linspace(-0.05, 0.6, 41)
+    for slope in (0, 1, 2):
+        exp = _lists(oracle.threshold_iterate_1d(d, offs, slope, 0.02, 0.03, 0.5, 0.45))
+        assert refine.thresholdIterate1D(d, offs, slope, 0.02, 0.03, 0.5, 0.45) == exp
+        assert len(exp[0]) > 1000
+    xm = np.linspace(0.01, 0.7, 37).astype(np.float32)
+    assert refine.thresholdIterate2D(d, xm, 0.4) == _lists(oracle.threshold_iterate_2d(d, xm, 0.4))
+    assert refine.thresholdIterate1D(d[:0], offs, 2, 0.0, 0.0, 0.5, 0.5) == ([], [], [])
+    with pytest.raises(RuntimeError):
+        refine.thresholdIterate1D(d, offs[::-1], 2, 0.0, 0.0, 0.5, 0.5)
+    exp = oracle.generate_all_tuples(n, 0, True, 2)
+    assert refine.generateAllTuples(n, 0, True, 2) == list(zip(exp[0].tolist(), exp[1].tolist()))
+    # kNN on a square from the long->square kernel, and on wide rows (radix select over 3000 candidates, k up to 300)
+    sq = np.round(rng.random((900, 900)), 2).astype(np.float32)
+    for k in (1, 7, 300):
+        assert refine.get_kNN_distances(sq, k) == _lists(oracle.get_knn_distances(sq, k))
+    wide = np.round(rng.random((50, 3000)), 2).astype(np.float32)
+    assert refine.get_kNN_distances(wide, 64) == _lists(oracle.get_knn_distances(wide, 64))
+    few = rng.random((5, 4)).astype(np.float32)                     # fewer candidates than kNN: zero padded
+    assert refine.get_kNN_distances(few, 6) == _lists(oracle.get_knn_distances(few, 6))
+    ci, cj, cd = oracle.get_knn_distances(sq, 20)
+    for rec in (False, True):
+        for cu in (False, True):
+            exp = _lists(oracle.lower_rank(ci, cj, cd, 900, 5, rec, cu, 0.02))
+            assert refine.lowerRank((ci, cj, cd), 900, 5, rec, cu, 0.02) == exp
+    qr = np.round(rng.random((900, 33)), 2).astype(np.float32)
+    qq = np.round(rng.random((33, 33)), 2).astype(np.float32)
+    for k in (1, 10, 40):
+        assert refine.extend((ci, cj, cd), qq, qr, k) == _lists(oracle.extend(ci, cj, cd, qq, qr, k))
