@@ -3,12 +3,14 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -837,15 +839,61 @@ struct Workspace {
         *out = e.first;
         return PPB_OK;
     }
+    // pinned host staging buffers (results bound for PAGEABLE caller memory), same grow-only policy
+    std::map<std::pair<int, int>, std::pair<void *, size_t>> pinned;
+    int get_pinned(int dev, int slot, size_t bytes, void **out) {
+        auto &e = pinned[{dev, slot}];
+        if (e.second < bytes || !e.first) {
+            if (e.first) cudaFreeHost(e.first);
+            e.first = nullptr;
+            e.second = 0;
+            if (cudaHostAlloc(&e.first, std::max<size_t>(bytes, 256), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(PPB_ERR_NOMEM, "cudaHostAlloc failed for " + std::to_string(bytes) + " bytes");
+            }
+            e.second = std::max<size_t>(bytes, 256);
+        }
+        *out = e.first;
+        return PPB_OK;
+    }
     void release() {
         for (auto &kv : slots)
             if (kv.second.first) cudaFree(kv.second.first);
         slots.clear();
+        for (auto &kv : pinned)
+            if (kv.second.first) cudaFreeHost(kv.second.first);
+        pinned.clear();
     }
 };
 Workspace g_ws;
 constexpr size_t kHostRing = 8;  // result buffers of the host-buffer path (chunks in flight between kernel and D2H)
 enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
+
+// true when the CUDA driver can DMA straight into p (pinned / registered / managed host memory)
+bool is_dma_able(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+// memcpy split over a few threads: one core cannot take 50 GB/s out of a staging buffer into fresh pages
+void parallel_memcpy(void *dst, const void *src, size_t bytes, int threads) {
+    if (threads <= 1 || bytes < ((size_t)8 << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t piece = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) {
+        const size_t off = (size_t)t * piece;
+        if (off >= bytes) break;
+        pool.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, std::min(piece, bytes - off)); });
+    }
+    std::memcpy(dst, src, std::min(piece, bytes));
+    for (auto &th : pool) th.join();
+}
 
 struct Stream {
     cudaStream_t s = nullptr;
@@ -929,7 +977,12 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
     size_t free_b = 0, total_b = 0;
     PPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    int64_t cap = (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per buffer
+    // Results bound for pageable memory (a plain NumPy array) are staged: D2H into a pinned ring, then a consumer
+    // thread memcpy's each chunk out with a few threads while the GPU works on the next ones.  A direct
+    // cudaMemcpyAsync into pageable memory would be staged by the driver, serially, at a fraction of the link rate.
+    const bool staged = (out && !is_dma_able(out)) || (labels && !is_dma_able(labels));
+    int64_t cap = staged ? (int64_t)1 << 24   // 128 MiB of float2 per pinned staging buffer
+                         : (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per buffer
     if (const char *e = std::getenv("PPB_HOST_CHUNK_ROWS")) cap = std::max<int64_t>(1024, atoll(e));
     while (cap > 1024 && (size_t)(2 * cap * per_row) > free_b / 2) cap >>= 1;
     std::vector<std::pair<int64_t, int64_t>> chunks;
@@ -942,13 +995,17 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     n_buf = std::max(1, std::min<int>(n_buf, (int)chunks.size()));
     const bool trace = std::getenv("PPB_HOST_TRACE") != nullptr;
 
-    void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {};
+    void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {}, *h_out[kHostRing] = {}, *h_lab[kHostRing] = {};
     Event done_compute[kHostRing], done_copy[kHostRing];
     for (int b = 0; b < n_buf; b++) {
         if (out)
             if (int rc = ws(WS_OUT0 + b, (size_t)max_chunk * rb, &d_out[b])) return rc;
         if (labels)
             if (int rc = ws(WS_LAB0 + b, (size_t)max_chunk, &d_lab[b])) return rc;
+        if (staged && out)
+            if (int rc = g_ws.get_pinned(device_id, b, (size_t)max_chunk * rb, &h_out[b])) return rc;
+        if (staged && labels)
+            if (int rc = g_ws.get_pinned(device_id, (int)kHostRing + b, (size_t)max_chunk, &h_lab[b])) return rc;
         PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
         PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
     }
@@ -960,6 +1017,55 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
         PPB_CUDA(cudaEventCreate(&tr_start));
         PPB_CUDA(cudaEventRecord(tr_start, s_compute.s));
     }
+    // staged mode: per-chunk "landed in the pinned ring" events, and the consumer thread that empties the ring
+    std::vector<cudaEvent_t> landed(staged ? chunks.size() : 0, nullptr);
+    for (auto &e : landed) PPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t n_enqueued = 0, n_consumed = 0;  // chunks whose D2H is enqueued / whose staging slot is free again
+    bool abort_consumer = false, consumer_failed = false;
+    const int copy_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    std::thread consumer;
+    if (staged)
+        consumer = std::thread([&] {
+            cudaSetDevice(device_id);
+            for (size_t c = 0; c < chunks.size(); c++) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return n_enqueued > c || abort_consumer; });
+                    if (abort_consumer) return;
+                }
+                if (cudaEventSynchronize(landed[c]) != cudaSuccess) consumer_failed = true;
+                const int b = (int)(c % n_buf);
+                const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
+                if (out && !consumer_failed)
+                    parallel_memcpy((char *)out + (size_t)(r0 - row_begin) * rb, h_out[b], (size_t)(r1 - r0) * rb, copy_threads);
+                if (labels && !consumer_failed) parallel_memcpy(labels + (r0 - row_begin), h_lab[b], (size_t)(r1 - r0), copy_threads);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    n_consumed = c + 1;
+                }
+                cv.notify_all();
+            }
+        });
+    struct ConsumerJoin {  // every exit path below stops and joins the consumer
+        std::thread &t;
+        std::mutex &mu;
+        std::condition_variable &cv;
+        bool &abort_flag;
+        bool finished = false;
+        ~ConsumerJoin() {
+            if (!t.joinable()) return;
+            if (!finished) {
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    abort_flag = true;
+                }
+                cv.notify_all();
+            }
+            t.join();
+        }
+    } joiner{consumer, mu, cv, abort_consumer};
     for (size_t c = 0; c < chunks.size(); c++) {
         const int b = (int)(c % n_buf);
         const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
@@ -975,19 +1081,37 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
         PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
         PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
         if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 2], s_copy.s));
+        if (staged && c >= (size_t)n_buf) {  // staging slot b must have been emptied by the consumer
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return n_consumed + n_buf > c; });
+        }
         if (out)
-            PPB_CUDA(cudaMemcpyAsync((char *)out + (size_t)(r0 - row_begin) * rb, d_out[b], (size_t)(r1 - r0) * rb,
-                                     cudaMemcpyDeviceToHost, s_copy.s));
+            PPB_CUDA(cudaMemcpyAsync(staged ? h_out[b] : (void *)((char *)out + (size_t)(r0 - row_begin) * rb), d_out[b],
+                                     (size_t)(r1 - r0) * rb, cudaMemcpyDeviceToHost, s_copy.s));
         if (labels)
-            PPB_CUDA(cudaMemcpyAsync(labels + (r0 - row_begin), d_lab[b], (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
-                                     s_copy.s));
+            PPB_CUDA(cudaMemcpyAsync(staged ? h_lab[b] : (void *)(labels + (r0 - row_begin)), d_lab[b], (size_t)(r1 - r0),
+                                     cudaMemcpyDeviceToHost, s_copy.s));
         if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 3], s_copy.s));
         PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
+        if (staged) {
+            PPB_CUDA(cudaEventRecord(landed[c], s_copy.s));
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                n_enqueued = c + 1;
+            }
+            cv.notify_all();
+        }
     }
     unsigned long long deg = 0;
     PPB_CUDA(cudaMemcpyAsync(&deg, d_deg, 8, cudaMemcpyDeviceToHost, s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_compute.s));
     PPB_CUDA(cudaStreamSynchronize(s_copy.s));
+    if (staged) {
+        joiner.finished = true;
+        consumer.join();
+        for (auto &e : landed) cudaEventDestroy(e);
+        if (consumer_failed) return fail(PPB_ERR_CUDA, "ppb_query_host: a device-to-host copy failed");
+    }
     if (trace) {  // one line per chunk on stderr: when its kernel and its copy ran, relative to the first launch
         double k_sum = 0, c_sum = 0;
         for (size_t c = 0; c < chunks.size(); c++) {

@@ -289,3 +289,27 @@ def test_multigpu_paths_match_single_gpu(eng):
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "multigpu_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- host path: launch plan, ring wrap, staged copy-out
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_path_many_chunks_ring_wraps(eng, oracle, monkeypatch, pinned):
+    """ppb_query_host with a tiny chunk cap: dozens of row-tile-aligned launches through the 8-deep buffer ring,
+    result and labels either DMA'd straight into pinned memory or staged and memcpy'd out to pageable memory."""
+    import torch
+    ref, qry = _sk(333, 16), _sk(150, 16, sample_seed=1)
+    bnd = (2, 0.02, 0.2, 1.0, 1.0)
+    exp_s, lab_s, nd_s = oracle.query(ref, None, KMERS, boundary=bnd)
+    exp_r, lab_r, nd_r = oracle.query(ref, qry, KMERS, boundary=bnd)
+    monkeypatch.setenv("PPB_HOST_CHUNK_ROWS", "3000")        # 19 launches (self), 17 (rectangle): the ring wraps twice
+    for q, exp, lab_o, nd_o in ((None, exp_s, lab_s, nd_s), (qry, exp_r, lab_r, nd_r)):
+        out = None
+        if pinned:
+            out = torch.empty(exp.shape, dtype=torch.float32, pin_memory=True).numpy()
+        got, lab, nd = eng.query_host(ref, q, KMERS, boundary=bnd, out=out)
+        assert np.abs(got - exp).max() <= TOL and nd == nd_o
+        same = (got == exp).all(axis=1)
+        assert (lab[same] == lab_o[same]).all()
+        b, e = 1234, exp.shape[0] - 777                          # a shard that starts and ends inside row tiles
+        part, _, _ = eng.query_host(ref, q, KMERS, row_begin=b, row_end=e)
+        assert (part == got[b:e]).all()

@@ -198,3 +198,29 @@ def test_sharded_allgather_gloo_world2(tmp_path, oracle):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_dist_pickle_roundtrip_and_row_order(tmp_path, lib):
+    """N4: <prefix>.dists.pkl/.npy as PopPUNK/utils.py:135-197 writes them, and the row <-> pair conventions
+    (utils.py:199-261) agree with the C ABI's index maps."""
+    import pickle
+    from poppunk_b200 import utils
+    names = [f"s{i}" for i in range(7)]
+    X = np.arange(42, dtype=np.float32).reshape(21, 2)
+    prefix = str(tmp_path / "db.dists")
+    utils.storePickle(names, names, True, X, prefix)
+    assert pickle.load(open(prefix + ".pkl", "rb")) == [names, names, True]     # what the reference's reader expects
+    r, q, self_, Y = utils.readPickle(prefix, enforce_self=True)
+    assert (r, q, self_) == (names, names, True) and Y.dtype == np.float32 and (Y == X).all()
+    assert utils.readPickle(prefix, distances=False)[3] is None
+    utils.storePickle(names[:3], names[3:], False, None, prefix)
+    with pytest.raises(SystemExit):
+        utils.readPickle(prefix, enforce_self=True)
+    rows = list(utils.listDistInts(names, names, True))
+    assert len(rows) == 21
+    for k, (j, i) in enumerate(rows):
+        assert lib.ppb_square_to_condensed(i, j, 7) == k and lib.ppb_calc_row_idx(k, 7) == i
+    assert list(utils.iterDistRows(names, names, True))[:2] == [("s1", "s0"), ("s2", "s0")]
+    assert list(utils.listDistInts(names[:2], names[2:5], False)) == [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
+    with pytest.raises(RuntimeError):
+        list(utils.iterDistRows(names, names[:3], True))
