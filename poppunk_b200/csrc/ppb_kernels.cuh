@@ -46,6 +46,9 @@ constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
 #ifndef PPB_EPI_WARPS
 #define PPB_EPI_WARPS 4
 #endif
+#ifndef PPB_EARLY_TEST
+#define PPB_EARLY_TEST 0
+#endif
 #ifndef PPB_ROLE_SHIFT
 #define PPB_ROLE_SHIFT 0
 #endif
@@ -65,7 +68,13 @@ static_assert(kThreads == 512 && PPB_ROLE_SHIFT % 4 == 0, "the role rotation ass
 // (setmaxnreg): helpers shrink, the two compute warpgroups grow back to what the register-stationary tile needs.
 // Conservation inside the CTA's pool: 8 x 168 + 4 x 88 + 4 x 24 <= 16 x 128 (warps 13-15 only give registers back;
 // the compute branch needs ~150, measured: 200 brings nothing).
-constexpr int kRegsCompute = 168, kRegsHelper = 88, kRegsProducer = 24;
+#ifndef PPB_REGS_COMPUTE
+#define PPB_REGS_COMPUTE 168
+#endif
+#ifndef PPB_REGS_HELPER
+#define PPB_REGS_HELPER 88
+#endif
+constexpr int kRegsCompute = PPB_REGS_COMPUTE, kRegsHelper = PPB_REGS_HELPER, kRegsProducer = 24;
 static_assert(kEpiWarps == 4 && kComputeWarps * kRegsCompute + 4 * kRegsHelper + 4 * kRegsProducer <= 16 * 128,
               "setmaxnreg: the compute warps can only grow by what the helper warpgroups give back");
 constexpr int kPad = 128;                          // genome padding of packed arrays
@@ -554,6 +563,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
+#if PPB_EARLY_TEST
+    bool next_ready = false;
+#endif
     // Two compute warps share a scheduler (w and w+4).  Started together they reach every k boundary together and
     // the ALU pipe idles while both reload their 112 row-genome registers from L2; started a few pipeline stages
     // apart (the ring allows kStages), one of them always has LOP3s to issue while the other reloads.
@@ -596,11 +608,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+#if PPB_EARLY_TEST
+                if (!next_ready) mbar_wait(&full[s], ph);
+#else
                 mbar_wait(&full[s], ph);
+#endif
                 const uint8_t *sb = stage_base + s * kStageBytes;
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
 #pragma unroll kJJUnroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
+#if PPB_EARLY_TEST
+                    // probe the NEXT stage's barrier under the LOP3 stream of this stage's last column: the probe's
+                    // latency (tens of cycles) is then never waited for at the top of a stage
+                    if (jj == kJB - 1) next_ready = mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
+#endif
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];

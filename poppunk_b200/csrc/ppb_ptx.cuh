@@ -30,7 +30,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 // the epilogue warps' spin loops, competing with the LOP3 stream for issue slots).  PPB_WAIT_HINT_NS > 0 passes
 // that suspend-time hint, so a waiting warp issues nothing until its barrier flips.
 #ifndef PPB_WAIT_HINT_NS
-#define PPB_WAIT_HINT_NS 0
+#define PPB_WAIT_HINT_NS 1000000  // measured: 736.6 vs 744.6 ms at N=100k (profiles/r01_experiments.md)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #if PPB_WAIT_HINT_NS > 0 && !defined(PPB_WAIT_HINT_RELAXED_ONLY)
@@ -58,6 +58,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 #endif
+}
+
+// non-blocking probe of a phase (acquire on success): lets a warp learn early that the NEXT ring stage has landed
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 
 // Same, for warps that are NOT on the critical path (TMA producer, epilogue).
