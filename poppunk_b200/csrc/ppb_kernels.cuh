@@ -46,9 +46,6 @@ constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
 #ifndef PPB_EPI_WARPS
 #define PPB_EPI_WARPS 4
 #endif
-#ifndef PPB_EARLY_TEST
-#define PPB_EARLY_TEST 0
-#endif
 #ifndef PPB_ROLE_SHIFT
 #define PPB_ROLE_SHIFT 0
 #endif
@@ -66,10 +63,11 @@ constexpr int kThreads = (kComputeWarps + 2 * 4) * 32;
 static_assert(kThreads == 512 && PPB_ROLE_SHIFT % 4 == 0, "the role rotation assumes 16 warps in 4 warpgroups");  // 4 full warpgroups: setmaxnreg is a warpgroup-wide operation
 // 13 warps put four on scheduler 0, i.e. 128 registers per thread at launch; the warpgroups then trade registers
 // (setmaxnreg): helpers shrink, the two compute warpgroups grow back to what the register-stationary tile needs.
-// Conservation inside the CTA's pool: 8 x 168 + 4 x 88 + 4 x 24 <= 16 x 128 (warps 13-15 only give registers back;
-// the compute branch needs ~150, measured: 200 brings nothing).
+// Conservation inside the CTA's pool: 8 x 200 + 4 x 88 + 4 x 24 = 16 x 128 exactly (warps 13-15 only give registers
+// back).  The compute branch holds ~150 live values; ptxas schedules against the setmaxnreg budget, and the slack up to
+// 200 is what lets it load the next column's plane words before the current column's LOP3s have drained.
 #ifndef PPB_REGS_COMPUTE
-#define PPB_REGS_COMPUTE 168
+#define PPB_REGS_COMPUTE 200  // measured at N=100k: 168 -> 741.7 ms, 192 -> 737.3, 200 -> 719.9 (profiles/r01_variants_regs_100k.log)
 #endif
 #ifndef PPB_REGS_HELPER
 #define PPB_REGS_HELPER 88
@@ -563,9 +561,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
-#if PPB_EARLY_TEST
-    bool next_ready = false;
-#endif
     // Two compute warps share a scheduler (w and w+4).  Started together they reach every k boundary together and
     // the ALU pipe idles while both reload their 112 row-genome registers from L2; started a few pipeline stages
     // apart (the ring allows kStages), one of them always has LOP3s to issue while the other reloads.
@@ -608,20 +603,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-#if PPB_EARLY_TEST
-                if (!next_ready) mbar_wait(&full[s], ph);
-#else
                 mbar_wait(&full[s], ph);
-#endif
                 const uint8_t *sb = stage_base + s * kStageBytes;
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
 #pragma unroll kJJUnroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
-#if PPB_EARLY_TEST
-                    // probe the NEXT stage's barrier under the LOP3 stream of this stage's last column: the probe's
-                    // latency (tens of cycles) is then never waited for at the top of a stage
-                    if (jj == kJB - 1) next_ready = mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
-#endif
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];

@@ -60,17 +60,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 }
 
-// non-blocking probe of a phase (acquire on success): lets a warp learn early that the NEXT ring stage has landed
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-
 // Same, for warps that are NOT on the critical path (TMA producer, epilogue).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
 #if PPB_WAIT_HINT_NS > 0
