@@ -1,10 +1,17 @@
-"""GPU twin of the one ``poppunk_refine`` function on the hot path: ``assignThreshold``.
+"""GPU twin of the reference's ``poppunk_refine`` extension module (src/python_bindings.cpp:79-136): the consumers of
+the (n_pairs, 2) distance array.  Same function names, argument order and return objects, so
+``import poppunk_b200.refine as poppunk_refine`` is the swap.
 
-Reference: src/boundary.cpp:42-80 (line_dist, assign_threshold), bound at src/python_bindings.cpp:18-25,
-79-83 with ``distMat`` as a ``.noconvert()`` Eigen ref — i.e. the array must already be float32 and
-C-contiguous; called from PopPUNK/models.py:1085-1089 as ``assignThreshold(X/self.scale, slope, x_max, y_max)``.
-The fused form (labels straight from the distance kernel, no (n,2) round trip) is
-``poppunk_b200.engine.query(..., boundary=(slope, x_max, y_max, scale_x, scale_y))``.
+    assignThreshold                      src/boundary.cpp:42-80     (hot path; fused form: engine.query(..., boundary=))
+    edgeThreshold / generateTuples /
+    generateAllTuples                    src/boundary.cpp:82-149
+    thresholdIterate1D / 2D              src/boundary.cpp:151-237
+    get_kNN_distances / lowerRank /
+    extend                               src/extend.cpp:52-289
+
+``distMat`` arguments must already be float32 and C-contiguous, as the reference's ``.noconvert()`` bindings demand.
+Every function runs on the GPU through the C ABI (include/ppb.h); there is no CPU path.  Results are bit-identical to
+the reference's own sources compiled into oracle/_ref (tests/golden/refine_ref.npz).
 """
 from __future__ import annotations
 
