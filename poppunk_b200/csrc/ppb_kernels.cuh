@@ -443,25 +443,24 @@ __device__ __forceinline__ uint32_t pack2(uint32_t lo, uint32_t hi) {  // lo + h
     asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
     return r;
 }
-// lane 0 stores (or adds) this warp's 8 uint16 counts of one column: one predicated 16-byte shared store
+// lane 0 stores this warp's 8 uint16 counts of one column: one predicated 16-byte shared store.  When a sketch has
+// several 32-group slices per k (S > 1024) the counts of the later slices ADD to what the earlier ones stored: every
+// lane has read the old value with a broadcast LDS.128 at the top of the column (`old`, latency hidden under the LOP3
+// stream) and folds it in with IMADs (FMA pipe) — no branch, so the LOP3 stream keeps its shape.
 template <bool kAccumulate>
 __device__ __forceinline__ void store_counts(uint32_t dst, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3,
-                                             uint32_t lane, uint32_t accumulate) {
+                                             uint32_t lane, uint32_t accumulate, const uint4 &old) {
     if (kAccumulate) {
-        if (lane == 0) {
-            if (accumulate) {
-                uint32_t o0, o1, o2, o3;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(dst));
-                r0 += o0, r1 += o1, r2 += o2, r3 += o3;
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
-        }
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(dst),
-            "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(lane)
-            : "memory");
+        const uint32_t f = accumulate ? 1u : 0u;
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r0) : "r"(old.x), "r"(f));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r1) : "r"(old.y), "r"(f));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r2) : "r"(old.z), "r"(f));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r3) : "r"(old.w), "r"(f));
     }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(dst),
+        "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(lane)
+        : "memory");
 }
 
 struct SmemLayout {
@@ -608,6 +607,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
 #pragma unroll kJJUnroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
+                    uint4 old = make_uint4(0u, 0u, 0u, 0u);
+                    if (!kSingleSlice) old = lds128(pdst);  // what earlier slices of this k stored for the previous column
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                         }
                         c[4] = __popc(x0), c[5] = __popc(x1), c[6] = __popc(x2), c[7] = __popc(x3);
                     }
-                    store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
+                    store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
                     // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
                     pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]), pk2 = pack2(c[4], c[5]), pk3 = pack2(c[6], c[7]);
                     pdst = dst;
@@ -652,7 +653,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         }
         {  // drain the pipeline: the tile's last column
             const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
-            store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc);
+            uint4 old = make_uint4(0u, 0u, 0u, 0u);
+            if (!kSingleSlice) old = lds128(pdst);
+            store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&cfull[cb]);  // release: this warp's counts of the tile are visible

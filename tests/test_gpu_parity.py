@@ -275,6 +275,46 @@ def test_cfg2_full_size_properties(eng, oracle):
         assert np.abs(host[b:b + 4000] - exp).max() <= TOL
 
 
+# ---------------------------------------------------------------- BASELINE config 3 (the north-star size) on one GPU
+def test_cfg3_north_star_size_properties(eng, oracle):
+    """100k genomes, S=1024, K=5: 4 999 950 000 rows (> 2^32, 40 GB of float2).  Size-independent properties plus the
+    oracle on sampled row ranges: first/last rows, both sides of row 2^32 (64-bit row arithmetic), row-tile and
+    genome-row boundaries; a block of the triangle must equal the rectangular query of the same genomes; a shard cut
+    inside row tiles must reproduce its slice of the full result."""
+    import torch
+    n = 100_000
+    total = n * (n - 1) // 2
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < total * 8 + (8 << 30):
+        pytest.skip("needs ~50 GB of free device memory")
+    kmers = np.array([13, 17, 21, 25, 29], dtype=np.int32)
+    sk = synth.synth_sketches_torch(n, kmers, 16, seed=42, device="cuda")
+    packed = eng.pack(sk)
+    out, _, ndeg = eng.query(packed, None, kmers)
+    torch.cuda.synchronize()
+    assert out.shape == (total, 2) and total > 2 ** 32
+    mn, mx = out.aminmax()
+    assert float(mn) >= 0.0 and float(mx) < 1.0 and not bool(torch.isnan(out[::997]).any())
+    ref_host = sk.cpu().numpy().view(np.uint64)
+    i_mid = oracle.calc_row_idx(2 ** 32, n)
+    starts = [0, total - 3000, 2 ** 32 - 1500, oracle.square_to_condensed(i_mid, i_mid + 1, n) - 1500,
+              oracle.square_to_condensed(64 * 700, 64 * 700 + 1, n) - 1500, oracle.square_to_condensed(99_935, 99_936, n) - 1500]
+    for b in starts:
+        exp, _ = oracle.query(ref_host, None, kmers, row_begin=int(b), row_end=int(b) + 3000)
+        got = out[b:b + 3000].cpu().numpy()
+        assert np.abs(got - exp).max() <= TOL, b
+    # triangle block == rectangle of the same genomes: rows (i, j) with i in [70000, 70064), j in [90000, 90200)
+    qi, rj = np.arange(70_000, 70_064), np.arange(90_000, 90_200)
+    rect, _, _ = eng.query(eng.pack(sk, idx=rj), eng.pack(sk, idx=qi), kmers)     # row = q * 200 + r
+    rows = torch.as_tensor([[oracle.square_to_condensed(int(i), int(j), n) for j in rj] for i in qi], device=out.device)
+    assert bool((out[rows.reshape(-1)] == rect).all())
+    # a shard that starts and ends inside row tiles reproduces its slice bit for bit
+    b, e = 2 ** 32 - 12_345_678, 2 ** 32 + 23_456_789
+    part, _, _ = eng.query(packed, None, kmers, row_begin=b, row_end=e)
+    assert bool((part == out[b:e]).all())
+    assert int(ndeg.item()) == 0
+
+
 # ---------------------------------------------------------------- multi-GPU (needs >= 2 devices; see tests/multigpu_check.py)
 def test_multigpu_paths_match_single_gpu(eng):
     """Spawns tests/multigpu_check.py under torchrun on 2 GPUs: NCCL all-gather path, fused peer-store exchange and
