@@ -243,6 +243,41 @@ def test_queryDatabase_dropin(eng, oracle, tmp_path):
     assert j.shape == (15, 5) and np.abs(j - exp_j).max() <= 1e-7
 
 
+# ---------------------------------------------------------------- BASELINE config 1: the reference's smoke-test genomes
+def test_cfg1_example_set_real_genomes(eng, oracle, golden_dir, tmp_path):
+    """The 29 assemblies of the reference's own smoke test (test/example_set.tar.bz2, test/run_test.py:20-21), sketched
+    with the stand-in sketcher (tools/standin_sketcher.c: reference schema, not pp-sketchlib's hash values), through the
+    drop-in queryDatabase: --create-db style all-vs-all, then the poppunk_assign style query-vs-ref call."""
+    from poppunk_b200 import sketchlib, utils
+    z = np.load(os.path.join(golden_dir, "example_set_sketches.npz"))
+    names, db_k, sk = [str(s) for s in z["names"]], z["kmers"], z["sketches"]
+    assert len(names) == 29 and names == sorted(names) and sk.shape == (29, len(db_k), 16 * 14)
+    prefix = str(tmp_path / "example_db")
+    sketchlib.write_db_npz(prefix, names, db_k, sk)
+    for klist in (np.arange(13, 30, 4), np.arange(13, 29, 3)):       # PopPUNK defaults; the smoke test's --k-step 3
+        kidx = [int(np.where(db_k == k)[0][0]) for k in klist]
+        d = sketchlib.queryDatabase(names, names, prefix, prefix, klist, self=True)
+        exp, _ = oracle.query(sk[:, kidx], None, klist.astype(np.int32))
+        assert d.shape == (406, 2) and d.dtype == np.float32 and np.abs(d - exp).max() <= TOL
+        # real-genome sanity: distances of one species, and an assembly against its own truncated copy
+        assert 0.0 <= d.min() and np.median(d[:, 0]) < 0.06 and np.median(d[:, 1]) < 0.3
+        rows = {pair: r for r, pair in enumerate(utils.iterDistRows(names, names, True))}
+        core, acc = d[rows[("12754_4#89_partial", "12754_4#89")]]
+        assert core < 0.03 and acc > 0.5                               # same sequence, 98 % of it missing
+    # assign-style: 5 of the genomes as queries against the other 24 (names must be disjoint, sketchlib.py:575-580)
+    qn, rn = names[::6], [n for i, n in enumerate(names) if i % 6]
+    qprefix = str(tmp_path / "query_db")
+    sketchlib.write_db_npz(qprefix, qn, db_k, sk[::6])
+    klist = np.arange(13, 30, 4)
+    kidx = [int(np.where(db_k == k)[0][0]) for k in klist]
+    d = sketchlib.queryDatabase(rn, qn, prefix, qprefix, klist, self=False)
+    ridx = [names.index(n) for n in rn]
+    exp, _ = oracle.query(sk[ridx][:, kidx], sk[::6][:, kidx], klist.astype(np.int32))
+    assert d.shape == (len(rn) * len(qn), 2) and np.abs(d - exp).max() <= TOL
+    with pytest.raises(SystemExit):
+        sketchlib.queryDatabase(names, qn, prefix, qprefix, klist, self=False)
+
+
 # ---------------------------------------------------------------- BASELINE config 2 at full size
 def test_cfg2_full_size_properties(eng, oracle):
     """10k genomes, S=1024, k={15,19,23,27,31}: 49 995 000 rows.  Checked by size-independent properties and
