@@ -264,3 +264,23 @@ def test_long_square_oracle(oracle):
     m = oracle.long_to_square_multi(rr, qr, qq, R, Q)
     assert (m[:R, :R] == oracle.long_to_square(rr, R)).all() and (m[R:, R:] == oracle.long_to_square(qq, Q)).all()
     assert (m[R:, :R] == qr.reshape(Q, R)).all() and (m == m.T).all()
+
+
+# ---------------------------------------------------------------- real genomes (BASELINE config 1 input)
+def test_example_set_fixture_oracle_vs_numpy(oracle, golden_dir):
+    """The stand-in sketches of the reference's 29 smoke-test assemblies (tests/golden/example_set_sketches.npz,
+    tools/make_cfg1_fixture.py): the C oracle and the NumPy restatement agree on counts and on (core, acc), and the
+    Jaccard spectrum is that of real genomes (truncation is exercised, nothing is degenerate)."""
+    z = np.load(os.path.join(golden_dir, "example_set_sketches.npz"))
+    db_k, sk = z["kmers"], z["sketches"]
+    assert int(z["sketchsize64"]) == 16 and int(z["bbits"]) == 14 and sk.dtype == np.uint64
+    klist = np.arange(13, 30, 4).astype(np.int32)
+    ref = np.ascontiguousarray(sk[:, [int(np.where(db_k == k)[0][0]) for k in klist]])
+    cnt, _ = oracle.query(ref, None, klist, out_mode=oracle.OUT_COUNTS)
+    assert (cnt == oracle.counts_numpy(ref)).all()
+    d, ndeg = oracle.query(ref, None, klist)
+    exp, ndeg_np = oracle.regress_numpy(cnt.astype(np.float64) / 1024.0, klist, 1024)
+    assert ndeg == ndeg_np == 0 and np.abs(d - exp).max() <= 1e-6
+    assert (cnt[:, -1] < 5).any() and (cnt[:, 0] >= 5).all()          # some series end early, none is empty
+    same = (cnt == 1024).all(axis=1)                                    # the set holds one assembly twice
+    assert same.sum() == 1 and (d[same] == 0).all() and 0.02 < np.median(d[:, 0]) < 0.06
