@@ -343,12 +343,16 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     const size_t smem = smem_need(tj);
     const bool single = p.n_slices == 1;
     static std::mutex attr_mu;
-    {
+    {   // function attributes are per device and sticky: set them once per device, not on every launch
+        static std::map<int, bool> attr_done;
         std::lock_guard<std::mutex> lk(attr_mu);
-        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (!attr_done[dev]) {
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_done[dev] = true;
+        }
     }
     // y-table for the fused fit (stream-ordered scratch; skipped when it would be unreasonably large)
     double *d_ytab = nullptr;
