@@ -23,6 +23,14 @@
 namespace {
 
 thread_local std::string g_err;
+// A host-buffer call launches the distance kernel once per row chunk with identical fit parameters: it lends the
+// launches ONE y-table buffer (filled by the first launch) instead of each launch allocating and filling its own.
+struct YtabLease {
+    double *buf = nullptr;
+    size_t capacity = 0;   // entries
+    bool filled = false;
+};
+thread_local YtabLease *g_ytab_lease = nullptr;
 std::atomic<int64_t> g_launches{0};
 
 int fail(int code, const std::string &msg) {
@@ -358,7 +366,18 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     double *d_ytab = nullptr;
     if (out_mode == PPB_OUT_DISTS) {
         const size_t entries = (size_t)(d_rand_table ? (size_t)n_clusters * n_clusters : 1) * K * ((size_t)p.S + 1);
-        if (entries * sizeof(double) <= ((size_t)64 << 20)) {
+        YtabLease *lease = g_ytab_lease;
+        if (lease && lease->buf && lease->capacity >= entries) {
+            if (!lease->filled) {
+                const int threads = 256;
+                const unsigned blocks = (unsigned)std::min<size_t>((entries + threads - 1) / threads, (size_t)sms * 8);
+                ppb::ytab_kernel<<<blocks, threads, 0, st>>>(p, lease->buf);
+                g_launches++;
+                PPB_CUDA(cudaGetLastError());
+                lease->filled = true;
+            }
+            p.ytab = lease->buf;
+        } else if (entries * sizeof(double) <= ((size_t)64 << 20)) {
             PPB_CUDA(cudaMallocAsync(&d_ytab, entries * sizeof(double), st));
             const int threads = 256;
             const unsigned blocks = (unsigned)std::min<size_t>((entries + threads - 1) / threads, (size_t)sms * 8);
@@ -871,7 +890,7 @@ struct Workspace {
 };
 Workspace g_ws;
 constexpr size_t kHostRing = 8;  // result buffers of the host-buffer path (chunks in flight between kernel and D2H)
-enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
+enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
 
 // true when the CUDA driver can DMA straight into p (pinned / registered / managed host memory)
 bool is_dma_able(const void *p) {
@@ -1021,6 +1040,21 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
         PPB_CUDA(cudaEventCreate(&tr_start));
         PPB_CUDA(cudaEventRecord(tr_start, s_compute.s));
     }
+    // one y-table for all launches of this call (same k-mers, table and sketch size throughout)
+    YtabLease lease;
+    if (out_mode == PPB_OUT_DISTS) {
+        const size_t entries = (size_t)(rand_table ? (size_t)n_clusters * n_clusters : 1) * K * ((size_t)64 * sketchsize64 + 1);
+        if (entries * sizeof(double) <= ((size_t)64 << 20)) {
+            void *q = nullptr;
+            if (int rc = ws(WS_YTAB, entries * sizeof(double), &q)) return rc;
+            lease.buf = (double *)q;
+            lease.capacity = entries;
+        }
+    }
+    struct LeaseScope {  // the lease is visible to the launches of THIS call only, whatever path leaves it
+        explicit LeaseScope(YtabLease *l) { g_ytab_lease = l; }
+        ~LeaseScope() { g_ytab_lease = nullptr; }
+    } lease_scope(lease.buf ? &lease : nullptr);
     // staged mode: per-chunk "landed in the pinned ring" events, and the consumer thread that empties the ring
     std::vector<cudaEvent_t> landed(staged ? chunks.size() : 0, nullptr);
     for (auto &e : landed) PPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
