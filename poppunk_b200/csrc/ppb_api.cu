@@ -208,10 +208,9 @@ int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, 
         return fail(PPB_ERR_ARG, "ppb_pack_dev: bad argument");
     if (!d_idx && n != n_src) return fail(PPB_ERR_ARG, "ppb_pack_dev: n != n_src without an index list");
     const int64_t n_pad = round_up(std::max<int64_t>(n, 1), ppb::kPad);
-    const int64_t total = (int64_t)K * n_slices_of(sketchsize64) * n_pad * ppb::kSliceWords;
-    const int threads = 256;
-    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, 148 * 64);
-    ppb::pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+    const int64_t units = (int64_t)K * n_slices_of(sketchsize64) * n_pad;  // one warp per 1792-byte unit
+    const int64_t blocks = std::min<int64_t>((units + ppb::kPackWarps - 1) / ppb::kPackWarps, 148 * 32);
+    ppb::pack_kernel<<<(unsigned)blocks, ppb::kPackWarps * 32, 0, (cudaStream_t)stream>>>(
         d_sketch, d_idx, n, n_pad, K, sketchsize64, n_slices_of(sketchsize64), d_packed);
     g_launches++;
     PPB_CUDA(cudaGetLastError());
@@ -509,7 +508,10 @@ int ppb_long_to_square_dev(const float *d_vec, int64_t stride, int64_t n, float 
     if (n < 0 || stride < 1 || (n > 0 && !d_square) || (n > 1 && !d_vec))
         return fail(PPB_ERR_ARG, "ppb_long_to_square_dev: bad argument");
     if (n == 0) return PPB_OK;
-    ppb::long_to_square_kernel<<<grid_for(n * n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_vec, stride, n, d_square);
+    {
+        const int64_t nt = (n + ppb::kSqTile - 1) / ppb::kSqTile;
+        ppb::long_to_square_kernel<<<grid_for(nt * (nt + 1) / 2, 1, 148 * 64), ppb::kSqTile * 8, 0, (cudaStream_t)stream>>>(d_vec, stride, n, d_square);
+    }
     g_launches++;
     PPB_CUDA(cudaGetLastError());
     return PPB_OK;
@@ -518,7 +520,7 @@ int ppb_long_to_square_dev(const float *d_vec, int64_t stride, int64_t n, float 
 int ppb_square_to_long_dev(const float *d_square, int64_t n, float *d_vec, void *stream) {
     if (n < 0 || (n > 1 && (!d_square || !d_vec))) return fail(PPB_ERR_ARG, "ppb_square_to_long_dev: bad argument");
     if (n < 2) return PPB_OK;
-    ppb::square_to_long_kernel<<<grid_for(n * (n - 1) / 2, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_square, n, d_vec);
+    ppb::square_to_long_kernel<<<grid_for(n - 1, 1, 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_square, n, d_vec);
     g_launches++;
     PPB_CUDA(cudaGetLastError());
     return PPB_OK;

@@ -120,36 +120,50 @@ struct QueryParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// pack: one thread per output word.
+// pack: one warp per (k-slice, genome) unit of 1792 B.  The unit's source words (its 16 uint64 columns x 14 planes,
+// contiguous in the canonical array when the slice is full) are read with coalesced 8-byte loads into shared
+// memory, permuted there, and written as one coalesced 1792-byte run: HBM-bound, 2 x 8960 B per genome.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(const uint64_t *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
-                            int64_t n_pad, int32_t K, int32_t ss64, int32_t n_slices,
-                            uint32_t *__restrict__ dst) {
-    const int64_t total = (int64_t)K * n_slices * n_pad * kSliceWords;
+constexpr int kPackWarps = 8;
+
+__global__ void __launch_bounds__(kPackWarps * 32) pack_kernel(const uint64_t *__restrict__ src,
+                                                               const int64_t *__restrict__ idx, int64_t n, int64_t n_pad,
+                                                               int32_t K, int32_t ss64, int32_t n_slices,
+                                                               uint32_t *__restrict__ dst) {
+    __shared__ uint32_t stage[kPackWarps][kSliceWords];  // [column-in-slice (16)][plane (14)][half (2)] as uint32
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t units = (int64_t)K * n_slices * n_pad;
     const int64_t W = (int64_t)ss64 * kBbits;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-         o += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t w = (int32_t)(o % kSliceWords);
-        const int64_t gk = o / kSliceWords;
-        const int64_t g = gk % n_pad;
-        const int32_t ks = (int32_t)(gk / n_pad);
+    uint32_t *sm = stage[warp];
+    for (int64_t u = (int64_t)blockIdx.x * kPackWarps + warp; u < units; u += (int64_t)gridDim.x * kPackWarps) {
+        const int64_t g = u % n_pad;
+        const int32_t ks = (int32_t)(u / n_pad);
         const int32_t k = ks / n_slices, sl = ks - k * n_slices;
-        int32_t lane, plane;
-        if (w < 384) {
-            lane = (w & 127) >> 2;
-            plane = ((w >> 7) << 2) + (w & 3);
-        } else {
-            lane = (w - 384) >> 1;
-            plane = 12 + (w & 1);
+        // uint64 columns 16*sl .. 16*sl+15 of this (genome, k): 224 consecutive words (fewer in the last slice)
+        const int32_t col0 = sl * 16, n_cols = max(0, min(16, ss64 - col0));
+        const int32_t n_words = g < n ? n_cols * kBbits : 0;
+        const uint64_t *base = nullptr;
+        if (g < n) base = src + ((idx ? idx[g] : g) * K + k) * W + (int64_t)col0 * kBbits;
+        __syncwarp();
+        for (int w = lane; w < kSliceWords / 2; w += 32) {
+            const uint64_t v = w < n_words ? __ldg(base + w) : 0ull;
+            sm[2 * w] = (uint32_t)v;
+            sm[2 * w + 1] = (uint32_t)(v >> 32);
         }
-        const int32_t grp = sl * 32 + lane;
-        uint32_t v = 0;
-        if (g < n && grp < 2 * ss64) {
-            const int64_t row = idx ? idx[g] : g;
-            const uint64_t word = src[(row * K + k) * W + (int64_t)(grp >> 1) * kBbits + plane];
-            v = (grp & 1) ? (uint32_t)(word >> 32) : (uint32_t)word;
+        __syncwarp();
+        uint32_t *out = dst + u * kSliceWords;
+        for (int o = lane; o < kSliceWords; o += 32) {
+            int32_t l, plane;  // output word o = plane `plane` of group (lane) `l`, see the layout comment above
+            if (o < 384) {
+                l = (o & 127) >> 2;
+                plane = ((o >> 7) << 2) + (o & 3);
+            } else {
+                l = (o - 384) >> 1;
+                plane = 12 + (o & 1);
+            }
+            // group l = half (l & 1) of column (l >> 1); staged word index = (column * 14 + plane) * 2 + half
+            out[o] = sm[(((l >> 1) * kBbits + plane) << 1) + (l & 1)];
         }
-        dst[o] = v;
     }
 }
 

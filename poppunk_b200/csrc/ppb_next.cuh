@@ -52,20 +52,23 @@ __device__ __forceinline__ void row_to_pair(const PairMap &m, int64_t row, int64
 }
 
 // ---- predicates -------------------------------------------------------------------------------------------
+// A predicate is split into load(row) and test(value) so that a thread can put all its loads in flight before the
+// first ballot (a ballot is a convergence point: written as one call, every load would wait for the previous vote).
 struct PredDists {  // edge_iterate: line_dist(...) <= 0   (boundary.cpp:82-95)
+    typedef float2 Value;
     const float2 *d;
     int32_t slope;
     float x_max, y_max;
-    __device__ __forceinline__ bool operator()(int64_t row) const {
-        const float2 v = d[row];
-        return line_dist(v.x, v.y, x_max, y_max, slope) <= 0.0f;
-    }
+    __device__ __forceinline__ float2 load(int64_t row) const { return __ldg(d + row); }
+    __device__ __forceinline__ bool test(const float2 &v) const { return line_dist(v.x, v.y, x_max, y_max, slope) <= 0.0f; }
 };
 template <typename T>
 struct PredLabels {  // generate_tuples: assignments[row] == within_label   (boundary.cpp:106)
+    typedef T Value;
     const T *labels;
     int32_t within;
-    __device__ __forceinline__ bool operator()(int64_t row) const { return (int32_t)labels[row] == within; }
+    __device__ __forceinline__ T load(int64_t row) const { return __ldg(labels + row); }
+    __device__ __forceinline__ bool test(const T &v) const { return (int32_t)v == within; }
 };
 
 // ---- ordered compaction -----------------------------------------------------------------------------------
@@ -85,10 +88,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(Pred pred, int64_t 
     const int64_t base = (int64_t)blockIdx.x * kSelBlockRows + (int64_t)warp * (32 * kSelIters);
     uint32_t ballots[kSelIters];
     uint32_t tot = 0;
+    typename Pred::Value vals[kSelIters];
+#pragma unroll
+    for (int m = 0; m < kSelIters; m++)  // 16 independent coalesced loads in flight per thread (clamped, branch-free)
+        vals[m] = pred.load(min(base + m * 32 + lane, n_rows - 1));
 #pragma unroll
     for (int m = 0; m < kSelIters; m++) {
-        const int64_t row = base + m * 32 + lane;
-        const bool sel = row < n_rows && pred(row);
+        const bool sel = base + m * 32 + lane < n_rows && pred.test(vals[m]);
         ballots[m] = __ballot_sync(0xffffffffu, sel);
         tot += __popc(ballots[m]);
     }
@@ -171,19 +177,47 @@ __global__ void rows_to_pairs_kernel(const int64_t *__restrict__ rows, int64_t n
 
 // ---- N2: long <-> square -----------------------------------------------------------------------------------
 // vec is read with an element stride (PopPUNK passes column views distMat[:, [c]] of the (n_pairs, 2) array).
-__global__ void long_to_square_kernel(const float *__restrict__ vec, int64_t stride, int64_t n,
-                                      float *__restrict__ sq) {
-    const int64_t total = n * n;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = o / n, c = o - r * n;
-        sq[o] = r == c ? 0.0f : vec[dev_sq2cond(min(r, c), max(r, c), n) * stride];
+// A condensed row is contiguous in j, so the upper triangle is read and written in coalesced runs; the lower
+// triangle is its transpose, produced through a 32 x 33 shared-memory tile so that it is written in coalesced runs
+// too (a direct gather would fetch one 32-byte sector per element).  Grid: 32 x 32 tiles with tile_c >= tile_r.
+constexpr int kSqTile = 32;
+
+__global__ void __launch_bounds__(kSqTile * 8) long_to_square_kernel(const float *__restrict__ vec, int64_t stride, int64_t n,
+                                                                     float *__restrict__ sq) {
+    __shared__ float tile[kSqTile][kSqTile + 1];
+    const int64_t nt = (n + kSqTile - 1) / kSqTile;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 4 rows each
+    for (int64_t t = blockIdx.x; t < nt * (nt + 1) / 2; t += gridDim.x) {
+        // t -> (tr, tc) with tc >= tr: row tr of the upper-triangular tile grid starts at tr*nt - tr(tr-1)/2
+        int64_t tr = (int64_t)((2.0 * (double)nt + 1.0 - sqrt((2.0 * (double)nt + 1.0) * (2.0 * (double)nt + 1.0) - 8.0 * (double)t)) * 0.5);
+        while (tr > 0 && tr * nt - tr * (tr - 1) / 2 > t) tr--;
+        while ((tr + 1) * nt - (tr + 1) * tr / 2 <= t) tr++;
+        const int64_t tc = tr + (t - (tr * nt - tr * (tr - 1) / 2));
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = tr * kSqTile + ty * 4 + k, c = tc * kSqTile + tx;
+            float v = 0.0f;
+            if (r < n && c < n && r != c) v = r < c ? vec[dev_sq2cond(r, c, n) * stride] : 0.0f;
+            if (r < n && c < n) {
+                if (r < c) sq[r * n + c] = v;
+                else if (r == c) sq[r * n + c] = 0.0f;
+            }
+            tile[ty * 4 + k][tx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // transposed tile: element (c, r) of the square, c in this tile's columns
+            const int64_t c = tc * kSqTile + ty * 4 + k, r = tr * kSqTile + tx;
+            if (c < n && r < n && r < c) sq[c * n + r] = tile[tx][ty * 4 + k];
+        }
     }
 }
+// one block per square row i: its j > i entries are one contiguous run of the condensed vector
 __global__ void square_to_long_kernel(const float *__restrict__ sq, int64_t n, float *__restrict__ vec) {
-    const int64_t total = n * (n - 1) / 2;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = dev_row_idx(k, n), j = dev_col_idx(k, i, n);
-        vec[k] = sq[i * n + j];
+    for (int64_t i = blockIdx.x; i < n - 1; i += gridDim.x) {
+        const int64_t base = dev_sq2cond(i, i + 1, n) - (i + 1);
+        for (int64_t j = i + 1 + threadIdx.x; j < n; j += blockDim.x) vec[base + j] = sq[i * n + j];
     }
 }
 // (R+Q)^2 square from: condensed ref-ref, query-major query-ref rectangle, condensed query-query

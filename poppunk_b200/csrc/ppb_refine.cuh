@@ -269,8 +269,9 @@ __global__ void iterate1d_sequential_kernel(const float2 *__restrict__ d, const 
 // The candidate list is a functor, so get_kNN_distances (a dense matrix row) and extend (dense query part
 // followed by the sparse / dense reference part) share the kernel.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kKnnThreads = 256;
+constexpr int kKnnThreads = 256;  // also the number of radix buckets: one thread folds one bucket
 constexpr int kKnnMax = 2048;
+static_assert(kKnnThreads == 256, "one thread per radix bucket when the per-warp histograms are folded");
 
 struct DenseRowCands {  // get_kNN_distances (extend.cpp:245-289): row r of a rows x cols matrix, j = column
     const float *mat;
@@ -310,31 +311,48 @@ struct ExtendCands {  // extend (extend.cpp:52-136): sample s < nr is a referenc
 template <typename Cands>
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_rows, int32_t knn, int64_t *__restrict__ out_i,
                                                           int64_t *__restrict__ out_j, float *__restrict__ out_d) {
-    __shared__ uint32_t hist[256];
+    __shared__ uint32_t hist[kKnnThreads / 32][256];  // one histogram per warp: 8x less contention on hot buckets
     __shared__ unsigned long long sel[kKnnMax];  // (key << 32 | position): positions < 2^32
     __shared__ uint32_t warp_cnt[kKnnThreads / 32];
-    __shared__ uint32_t s_prefix, s_need, s_below, s_taken_eq, s_n_sel;
+    __shared__ uint32_t s_prefix, s_need, s_below, s_taken_eq, s_n_sel, s_eq_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kBatch = 4;  // loads of a batch are issued together, before the first shared-memory atomic
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t len = c.length(r);
         // ---- (1) radix select of the knn-th smallest key among candidates with j != r
         uint32_t prefix = 0, need = (uint32_t)knn, below = 0;  // keys matching `prefix` in the decided bytes
         bool enough = true;
         for (int byte = 3; byte >= 0; byte--) {
-            for (int b = threadIdx.x; b < 256; b += kKnnThreads) hist[b] = 0;
+            for (int b = threadIdx.x; b < 256 * (kKnnThreads / 32); b += kKnnThreads) (&hist[0][0])[b] = 0;
             __syncthreads();
             const uint32_t decided = byte == 3 ? 0u : (0xffffffffu << (8 * (byte + 1)));
-            for (int64_t pos = threadIdx.x; pos < len; pos += kKnnThreads) {
-                if (c.j_of(r, pos) == r) continue;
-                const uint32_t key = float_key(c.dist(r, pos));
-                if ((key & decided) == (prefix & decided)) atomicAdd(&hist[(key >> (8 * byte)) & 255u], 1u);
+            for (int64_t p0 = threadIdx.x; p0 < len; p0 += (int64_t)kBatch * kKnnThreads) {
+                uint32_t key[kBatch];
+                bool use[kBatch];
+#pragma unroll
+                for (int q = 0; q < kBatch; q++) {
+                    const int64_t pos = p0 + (int64_t)q * kKnnThreads;
+                    use[q] = pos < len && c.j_of(r, pos) != r;
+                    key[q] = float_key(c.dist(r, min(pos, len - 1)));
+                }
+#pragma unroll
+                for (int q = 0; q < kBatch; q++)
+                    if (use[q] && (key[q] & decided) == (prefix & decided)) atomicAdd(&hist[warp][(key[q] >> (8 * byte)) & 255u], 1u);
+            }
+            __syncthreads();
+            {   // fold the per-warp histograms into hist[0]
+                uint32_t t = 0;
+#pragma unroll
+                for (int w = 0; w < kKnnThreads / 32; w++) t += hist[w][threadIdx.x];
+                __syncthreads();
+                hist[0][threadIdx.x] = t;
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 uint32_t acc = 0, b = 0;
                 for (; b < 256; b++) {
-                    if (acc + hist[b] >= need) break;
-                    acc += hist[b];
+                    if (acc + hist[0][b] >= need) break;
+                    acc += hist[0][b];
                 }
                 if (b == 256) {  // fewer than `need` candidates in total: take everything
                     s_need = 0xffffffffu;
@@ -342,6 +360,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
                     s_need = need - acc;
                     s_prefix = prefix | (b << (8 * byte));
                     s_below = below + acc;
+                    s_eq_total = hist[0][b];  // after the last byte: how many keys equal the threshold key
                 }
             }
             __syncthreads();
@@ -361,33 +380,56 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
             s_taken_eq = 0;
         }
         __syncthreads();
-        // ---- (2) collect
-        for (int64_t start = 0; start < len; start += kKnnThreads) {
-            const int64_t pos = start + threadIdx.x;
-            bool lt = false, eq = false;
-            uint32_t key = 0;
-            if (pos < len && c.j_of(r, pos) != r) {
-                key = float_key(c.dist(r, pos));
-                lt = !enough || key < prefix;
-                eq = enough && key == prefix;
-            }
-            const uint32_t beq = __ballot_sync(0xffffffffu, eq);
-            if (lane == 0) warp_cnt[warp] = __popc(beq);
-            __syncthreads();
-            uint32_t before = s_taken_eq;
-            for (int w = 0; w < warp; w++) before += warp_cnt[w];
-            const uint32_t rank = before + __popc(beq & ((1u << lane) - 1));
-            if (lt || (eq && rank < need)) {
-                const uint32_t at = atomicAdd(&s_n_sel, 1u);
-                if (at < kKnnMax) sel[at] = ((unsigned long long)key << 32) | (unsigned long long)(uint32_t)pos;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t t = 0;
-                for (int w = 0; w < kKnnThreads / 32; w++) t += warp_cnt[w];
-                s_taken_eq += t;
+        // ---- (2) collect.  Usually every key equal to the threshold is needed (no tie is cut), or everything is
+        // taken: then order does not matter before the sort and one batched pass with a slot counter does it.  Only
+        // when the threshold cuts THROUGH a run of ties are the first `need` of them, in position order, picked with
+        // the block-ordered ballot scan (three barriers per 256 candidates).
+        if (!enough || s_eq_total == need) {
+            for (int64_t p0 = threadIdx.x; p0 < len; p0 += (int64_t)kBatch * kKnnThreads) {
+                uint32_t key[kBatch];
+                bool use[kBatch];
+#pragma unroll
+                for (int q = 0; q < kBatch; q++) {
+                    const int64_t pos = p0 + (int64_t)q * kKnnThreads;
+                    use[q] = pos < len && c.j_of(r, pos) != r;
+                    key[q] = float_key(c.dist(r, min(pos, len - 1)));
+                }
+#pragma unroll
+                for (int q = 0; q < kBatch; q++)
+                    if (use[q] && (!enough || key[q] <= prefix)) {
+                        const uint32_t at = atomicAdd(&s_n_sel, 1u);
+                        if (at < kKnnMax) sel[at] = ((unsigned long long)key[q] << 32) | (unsigned long long)(uint32_t)(p0 + (int64_t)q * kKnnThreads);
+                    }
             }
             __syncthreads();
+        } else {
+            for (int64_t start = 0; start < len; start += kKnnThreads) {
+                const int64_t pos = start + threadIdx.x;
+                bool lt = false, eq = false;
+                uint32_t key = 0;
+                if (pos < len && c.j_of(r, pos) != r) {
+                    key = float_key(c.dist(r, pos));
+                    lt = key < prefix;
+                    eq = key == prefix;
+                }
+                const uint32_t beq = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) warp_cnt[warp] = __popc(beq);
+                __syncthreads();
+                uint32_t before = s_taken_eq;
+                for (int w = 0; w < warp; w++) before += warp_cnt[w];
+                const uint32_t rank = before + __popc(beq & ((1u << lane) - 1));
+                if (lt || (eq && rank < need)) {
+                    const uint32_t at = atomicAdd(&s_n_sel, 1u);
+                    if (at < kKnnMax) sel[at] = ((unsigned long long)key << 32) | (unsigned long long)(uint32_t)pos;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    uint32_t t = 0;
+                    for (int w = 0; w < kKnnThreads / 32; w++) t += warp_cnt[w];
+                    s_taken_eq += t;
+                }
+                __syncthreads();
+            }
         }
         const uint32_t n_sel = min(s_n_sel, (uint32_t)knn);
         // ---- (3) bitonic sort of sel[0 .. n_pow2)
