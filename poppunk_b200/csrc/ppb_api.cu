@@ -560,11 +560,29 @@ int ppb_assign_threshold_dev(const float *d_dists, int64_t n, int32_t slope, flo
 // ---------------------------------------------------------------------------------------------------------
 extern "C++" {
 namespace {
+// The stream-ordered allocator returns freed memory to the OS at every synchronisation unless told otherwise, and the
+// functions below take gigabytes of scratch per call (threshold iteration: ~25 B per row): keep it cached in the
+// device's default pool between calls.  ppb_release_workspace() trims the pool.
+void keep_scratch_cached() {
+    static std::mutex mu;
+    static std::map<int, bool> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[dev] = true;
+}
 // stream-ordered scratch that frees itself (also on the error paths)
 struct Scratch {
     cudaStream_t st;
     std::vector<void *> ptrs;
-    explicit Scratch(cudaStream_t s) : st(s) {}
+    explicit Scratch(cudaStream_t s) : st(s) { keep_scratch_cached(); }
     ~Scratch() {
         for (void *q : ptrs) cudaFreeAsync(q, st);
     }
@@ -1188,6 +1206,13 @@ int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t
 int ppb_release_workspace(void) {
     std::lock_guard<std::mutex> lk(g_ws.mu);
     g_ws.release();
+    int dev = 0;
+    cudaMemPool_t pool;  // the stream-ordered scratch cached by the iteration / kNN entry points
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
     return PPB_OK;
 }
 

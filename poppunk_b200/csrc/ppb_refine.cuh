@@ -63,15 +63,27 @@ __global__ void __launch_bounds__(kSelThreads) iterate2d_kernel(const float2 *__
         const int64_t row = base + m * 32 + lane;
         v[m] = row < n_rows ? d[row] : make_float2(0.f, 0.f);
     }
-    for (int o = 0; o < n_off; o++) {
-        const float xm = x_max[o], xp = o ? x_max[o - 1] : 0.f;
-        uint32_t tot = 0;
+    // in(o, row) is evaluated once per step: "outside boundary o-1" is the previous step's result, kept as one bit per
+    // row; the sloped form of line_dist is written out with its uniform product hoisted (same operations, same
+    // order as boundary.cpp:48-50), the sqrt form (a zero intercept) stays behind a uniform branch.
+    auto inside = [&](const float2 &p2, float xm, float prod, bool degenerate) -> bool {
+        const float side = degenerate ? line_dist(p2.x, p2.y, xm, y_max, 2)
+                                      : __fsub_rn(__fadd_rn(__fmul_rn(p2.y, xm), __fmul_rn(p2.x, y_max)), prod);
+        return side <= 0.0f;
+    };
+    uint32_t valid = 0;
 #pragma unroll
-        for (int m = 0; m < kSelIters; m++) {
-            const bool sel = base + m * 32 + lane < n_rows && line_dist(v[m].x, v[m].y, xm, y_max, 2) <= 0.0f &&
-                             (o == 0 || line_dist(v[m].x, v[m].y, xp, y_max, 2) > 0.0f);
-            tot += __popc(__ballot_sync(0xffffffffu, sel));
-        }
+    for (int m = 0; m < kSelIters; m++) valid |= (base + m * 32 + lane < n_rows ? 1u : 0u) << m;
+    uint32_t prev = 0;
+    for (int o = 0; o < n_off; o++) {
+        const float xm = x_max[o], prod = __fmul_rn(xm, y_max);
+        const bool degenerate = xm == 0.0f || y_max == 0.0f;
+        uint32_t cur = 0;
+#pragma unroll
+        for (int m = 0; m < kSelIters; m++) cur |= (inside(v[m], xm, prod, degenerate) ? 1u : 0u) << m;
+        const uint32_t admit = cur & ~prev & valid;
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, __popc(admit));  // the warp's admissions at this step
+        prev = cur;
         if (lane == 0) warp_tot[o][warp] = tot;
     }
     __syncthreads();
@@ -84,19 +96,26 @@ __global__ void __launch_bounds__(kSelThreads) iterate2d_kernel(const float2 *__
         }
         return;
     }
+    prev = 0;
     for (int o = 0; o < n_off; o++) {
         int64_t pos = cnt[(int64_t)o * n_blocks + blockIdx.x];
         for (int w = 0; w < warp; w++) pos += warp_tot[o][w];
-        const float xm = x_max[o], xp = o ? x_max[o - 1] : 0.f;
+        const float xm = x_max[o], prod = __fmul_rn(xm, y_max);
+        const bool degenerate = xm == 0.0f || y_max == 0.0f;
+        uint32_t cur = 0;
+#pragma unroll
+        for (int m = 0; m < kSelIters; m++) cur |= (inside(v[m], xm, prod, degenerate) ? 1u : 0u) << m;
+        const uint32_t admit = cur & ~prev & valid;
+        prev = cur;
+        if (warp_tot[o][warp] == 0) continue;  // nothing of this warp is admitted at this step (the common case)
 #pragma unroll
         for (int m = 0; m < kSelIters; m++) {
-            const int64_t row = base + m * 32 + lane;
-            const bool sel = row < n_rows && line_dist(v[m].x, v[m].y, xm, y_max, 2) <= 0.0f &&
-                             (o == 0 || line_dist(v[m].x, v[m].y, xp, y_max, 2) > 0.0f);
+            const bool sel = (admit >> m) & 1u;
             const uint32_t b = __ballot_sync(0xffffffffu, sel);
             if (sel) {
                 const int64_t at = pos + __popc(b & ((1u << lane) - 1));
                 if (at < capacity) {
+                    const int64_t row = base + m * 32 + lane;
                     const int64_t i = dev_row_idx(row, n_samples);
                     out_i[at] = i;
                     out_j[at] = dev_col_idx(row, i, n_samples);
