@@ -248,7 +248,7 @@ def test_cfg1_example_set_real_genomes(eng, oracle, golden_dir, tmp_path):
     """The 29 assemblies of the reference's own smoke test (test/example_set.tar.bz2, test/run_test.py:20-21), sketched
     with the stand-in sketcher (tools/standin_sketcher.c: reference schema, not pp-sketchlib's hash values), through the
     drop-in queryDatabase: --create-db style all-vs-all, then the poppunk_assign style query-vs-ref call."""
-    from poppunk_b200 import sketchlib, utils
+    from poppunk_b200 import distfiles as utils, sketchlib
     z = np.load(os.path.join(golden_dir, "example_set_sketches.npz"))
     names, db_k, sk = [str(s) for s in z["names"]], z["kmers"], z["sketches"]
     assert len(names) == 29 and names == sorted(names) and sk.shape == (29, len(db_k), 16 * 14)

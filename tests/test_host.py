@@ -204,7 +204,7 @@ def test_dist_pickle_roundtrip_and_row_order(tmp_path, lib):
     """N4: <prefix>.dists.pkl/.npy as PopPUNK/utils.py:135-197 writes them, and the row <-> pair conventions
     (utils.py:199-261) agree with the C ABI's index maps."""
     import pickle
-    from poppunk_b200 import utils
+    from poppunk_b200 import distfiles as utils
     names = [f"s{i}" for i in range(7)]
     X = np.arange(42, dtype=np.float32).reshape(21, 2)
     prefix = str(tmp_path / "db.dists")
