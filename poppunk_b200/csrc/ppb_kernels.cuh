@@ -13,7 +13,7 @@
 //     words [q*128 + l*4 + e], q=0..2, e=0..3 : plane 4q+e of lane l      (three conflict-free LDS.128)
 //     words [384 + l*2 + e],   e=0..1         : plane 12+e  of lane l      (one LDS.64)
 // and the whole array is  uint32 [K*n_slices][n_pad][448]  (k-slice-major, genome-minor), so the JB
-// consecutive genomes a pipeline stage needs are ONE contiguous 28 KB TMA bulk copy.
+// consecutive genomes a pipeline stage needs are ONE contiguous TMA bulk copy (4 genomes = 7 KB).
 //
 // MAPPING (why it looks like this — DESIGN.md has the numbers).  The work per pair is 14 LOP3 per group of
 // 32 bins and nothing else of weight, so the kernel is bound by the INT32 logic pipe, not by HBM.  Each
@@ -444,8 +444,8 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
 // ------------------------------------------------------------------------------------------------
 // The hot path.  Persistent CTAs (one per SM), warp-specialised:
 //   warps 0-7   compute: LOP3/POPC/REDUX stream, never leave it (count tile double-buffered)
-//   warp  8     TMA producer: 1-D bulk copies of column-genome slices into a 3-stage ring
-//   warps 9-11  epilogue: counts -> fit -> row-ordered stores of the previous tile, concurrently
+//   warps 8-11  epilogue (one per scheduler): counts -> fit -> row-ordered stores of the previous tile, concurrently
+//   warp  12    TMA producer: 1-D bulk copies of column-genome slices into the kStages-deep ring (13-15: fillers)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t redux_add(uint32_t v) {
     uint32_t r;
