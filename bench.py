@@ -115,11 +115,20 @@ def load_oracle():
     return oracle, native
 
 
+def host_threads():
+    """Every core this process may run on.  (torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
+    turn the reference arm of an N>1 launch into a single-thread run: the thread count is passed explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(oracle, native, ref_host, target_s=12.0):
     """Time rows [0, R) of the self job (R sized for ~target_s of CPU work).  Returns (pairs/s, cores, R)."""
     n = ref_host.shape[0]
     total = n * (n - 1) // 2
-    threads = oracle.max_threads()
+    threads = host_threads()
     probe = min(total, 200_000 * threads)
     t0 = time.perf_counter()
     oracle.query(ref_host, None, KMERS, row_begin=0, row_end=probe, threads=threads, native=native)
@@ -156,7 +165,7 @@ def run_reference(args):
         ref_host = host_sketches(min(n, 20_000))
     n_eff = ref_host.shape[0]
     total = n_eff * (n_eff - 1) // 2
-    threads = oracle.max_threads()
+    threads = host_threads()
     # size one step at ~8 s of CPU work
     probe = min(total, 200_000 * threads)
     t0 = time.perf_counter()
@@ -451,7 +460,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100_000, help="genomes (default: the north-star N=100k)")
+    ap.add_argument("--n", "--genomes", dest="n", type=int, default=100_000,
+                    help="genomes (default: the north-star N=100k); use --genomes under torchrun, whose own parser claims --n*")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -224,3 +224,23 @@ def test_dist_pickle_roundtrip_and_row_order(tmp_path, lib):
     assert list(utils.listDistInts(names[:2], names[2:5], False)) == [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
     with pytest.raises(RuntimeError):
         list(utils.iterDistRows(names, names[:3], True))
+
+
+def test_reference_arm_under_torchrun_uses_all_cores():
+    """`bench.py --impl reference` launched the way the driver launches N>1 runs: rank 0 alone prints ONE JSON line,
+    the other rank exits 0, and the CPU arm still uses every core (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--genomes", "2000"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
