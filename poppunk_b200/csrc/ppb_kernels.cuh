@@ -54,6 +54,18 @@ constexpr int kTI = kRowsPerWarp * kComputeWarps;  // 64 rows per tile
 #endif
 constexpr int kJB = PPB_JB;                        // column genomes per pipeline stage
 constexpr int kStages = PPB_STAGES;
+// PPB_DUAL_RING=1 (EXPERIMENT PREPARED FOR THE NEXT ROUND, NOT YET RUN ON HARDWARE; the default build is unchanged):
+// the two compute warps of a scheduler (w and w+4) get a TMA ring each and walk the k-slices of a tile in different
+// orders (the second group starts half-way round), so they never meet a stage boundary, a barrier release or the
+// row-genome reload at the same moment — the coincidence of those stalls is what the ncu capture blames for the idle
+// ALU cycles (profiles/r01_experiments.md).  Costs a second producer warp (a filler today) and a second ring: the two
+// count tiles (184 KB at K=5) and one 6-stage ring (43 KB) already fill shared memory, so build it with PPB_STAGES=3
+// (two 3-stage rings, same bytes) — with 6 stages per ring the host falls back to 64-column tiles.
+#ifndef PPB_DUAL_RING
+#define PPB_DUAL_RING 0
+#endif
+constexpr int kRings = PPB_DUAL_RING ? 2 : 1;
+constexpr int kAllStages = kRings * kStages;
 constexpr int kJJUnroll = PPB_JJ_UNROLL;           // column-loop unroll inside a stage
 constexpr int kStageBytes = kJB * kSliceBytes;     // 7168
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
@@ -484,10 +496,10 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(int K, int tj) {
     SmemLayout L;
     L.cnt_bytes = ((uint32_t)K * tj * kCntRowWords * 4 + 127u) & ~127u;
-    L.off_cnt = kStages * kStageBytes;
+    L.off_cnt = kAllStages * kStageBytes;
     L.off_rinfo = L.off_cnt + kCntBufs * L.cnt_bytes;
     L.off_bar = L.off_rinfo + kTI * (uint32_t)sizeof(RowInfo);
-    L.off_trash = L.off_bar + (2 * kStages + 2 * kCntBufs) * 8;
+    L.off_trash = L.off_bar + (2 * kAllStages + 2 * kCntBufs) * 8;
     L.total = L.off_trash + kComputeWarps * 16;
     return L;
 }
@@ -499,8 +511,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const SmemLayout L = smem_layout(p.K, p.tj);
     uint8_t *stage_base = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bar);
-    uint64_t *empty = full + kStages;
-    uint64_t *cfull = empty + kStages;    // count tile b complete (all compute warps arrived)
+    uint64_t *empty = full + kAllStages;
+    uint64_t *cfull = empty + kAllStages;    // count tile b complete (all compute warps arrived)
     uint64_t *cempty = cfull + kCntBufs;  // count tile b consumed (all epilogue warps arrived)
 
     // Role of a warp = its index rotated by PPB_ROLE_SHIFT warps.  The SM's warp arbiter favours the higher warp
@@ -509,9 +521,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     // leaves idle.  Warpgroups (setmaxnreg granularity) stay whole: the shift is a multiple of 4.
     const int warp = ((threadIdx.x >> 5) + PPB_ROLE_SHIFT) & 15, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < kAllStages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kComputeWarps);
+            mbar_init(&empty[s], kComputeWarps / kRings);  // the warps that consume this ring
         }
         for (int b = 0; b < kCntBufs; b++) {
             mbar_init(&cfull[b], kComputeWarps);
@@ -525,18 +537,31 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 
     if (warp >= kProducerWarp) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
-        if (warp > kProducerWarp) return;  // filler warps of the producer's warpgroup
-        // ===== TMA producer: streams column-genome slices of every (tile, k, slice) into the ring =====
+        if (warp >= kProducerWarp + kRings) return;  // filler warps of the producer's warpgroup
+        // ===== TMA producer (one per ring): streams column-genome slices of every (tile, k, slice) into its ring =====
         if (lane == 0) {
             const uint64_t pol_b = l2_policy(p.b_policy);
             uint32_t it = 0;
+#if PPB_DUAL_RING
+            const uint32_t ring_base = (uint32_t)(warp - kProducerWarp) * kStages;
+            const int ks_shift = (warp - kProducerWarp) * (p.K / 2) * p.n_slices;  // whole k's: slices of a k stay in order
+#endif
             for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const int2 tc = p.tiles[tile];
                 const int64_t j0 = (int64_t)tc.y * tj;
+#if PPB_DUAL_RING
+                for (int ksi = 0; ksi < KS; ksi++) {
+                    const int ks = ksi + ks_shift < KS ? ksi + ks_shift : ksi + ks_shift - KS;
+#else
                 for (int ks = 0; ks < KS; ks++) {
+#endif
                     const uint32_t *src = p.B + ((int64_t)ks * p.nB_pad + j0) * kSliceWords;
                     for (int jb = 0; jb < n_jb; jb++, it++) {
+#if PPB_DUAL_RING
+                        const uint32_t s = ring_base + it % kStages, ph = (it / kStages) & 1;
+#else
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+#endif
                         mbar_wait_relaxed(&empty[s], ph ^ 1, 100);
                         mbar_arrive_expect_tx(&full[s], kStageBytes);
                         tma_load_1d_hint(stage_base + s * kStageBytes, src + (int64_t)jb * kJB * kSliceWords,
@@ -574,6 +599,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
+#if PPB_DUAL_RING
+    const uint32_t ring_base = (uint32_t)(warp >> 2) * kStages;           // warps 0-3: ring 0, warps 4-7: ring 1
+    const int ks_shift = (warp >> 2) * (p.K / 2) * p.n_slices;            // the second group starts half-way round the k's
+#endif
     // Two compute warps share a scheduler (w and w+4).  Started together they reach every k boundary together and
     // the ALU pipe idles while both reload their 112 row-genome registers from L2; started a few pipeline stages
     // apart (the ring allows kStages), one of them always has LOP3s to issue while the other reloads.
@@ -591,7 +620,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;  // packed (2 x uint16) partial counts of the previous column
         uint32_t pdst = trash_addr, pacc = 0;          // where they go; whether they add to an earlier slice
 
+#if PPB_DUAL_RING
+        for (int ksi = 0; ksi < KS; ksi++) {
+            const int ks = ksi + ks_shift < KS ? ksi + ks_shift : ksi + ks_shift - KS;
+#else
         for (int ks = 0; ks < KS; ks++) {
+#endif
             const int k = kSingleSlice ? ks : ks / p.n_slices;
             const int sl = kSingleSlice ? 0 : ks - k * p.n_slices;
             const uint32_t valid = (sl * 32 + lane < p.G32) ? 0xffffffffu : 0u;
@@ -615,7 +649,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
             const uint32_t cnt_k = cnt_addr + k * tj * kCntRowWords * 4;
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
+#if PPB_DUAL_RING
+                const uint32_t s = ring_base + it % kStages, ph = (it / kStages) & 1;
+#else
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+#endif
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
