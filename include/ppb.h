@@ -238,6 +238,14 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref,
 int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,
                              int64_t cap_rows, int64_t *bounds, int64_t max_chunks);
 
+/* The tile schedule of one ppb_query_dev launch over [row_begin,row_end): (row tile, column tile) index pairs in
+ * execution order — row tiles are PPB_TILE_ROWS genomes of the row side, column tiles tile_cols reference genomes;
+ * bands of band_tiles row tiles, the column tile the slow index inside a band; self mode skips tiles with no j > i.
+ * Writes up to max_tiles pairs into tiles (int32 [2*max_tiles], may be NULL), returns the tile count or -1.  Host-only. */
+#define PPB_TILE_ROWS 64
+int64_t ppb_plan_tiles(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,
+                       int32_t tile_cols, int32_t band_tiles, int32_t *tiles, int64_t max_tiles);
+
 /* Frees the device workspace the host-buffer calls keep between invocations (grow-only, per device). */
 int ppb_release_workspace(void);
 

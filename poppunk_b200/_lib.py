@@ -21,7 +21,7 @@ SYMBOLS = [
     "ppb_edges_scratch_bytes", "ppb_edges_from_dists_dev", "ppb_edges_from_labels_dev", "ppb_long_to_square_dev",
     "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev", "ppb_plan_host_chunks",
     "ppb_generate_all_tuples_dev", "ppb_threshold_iterate_1d_dev", "ppb_threshold_iterate_2d_dev", "ppb_knn_dev",
-    "ppb_lower_rank_dev", "ppb_extend_dev",
+    "ppb_lower_rank_dev", "ppb_extend_dev", "ppb_plan_tiles",
 ]
 
 
@@ -105,6 +105,8 @@ def load():
     L.ppb_lower_rank_dev.restype = C.c_int
     L.ppb_extend_dev.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
     L.ppb_extend_dev.restype = C.c_int
+    L.ppb_plan_tiles.argtypes = [i64, i64, i32, i64, i64, i32, i32, vp, i64]
+    L.ppb_plan_tiles.restype = i64
     L.ppb_plan_host_chunks.argtypes = [i64, i64, i32, i64, i64, i64, vp, i64]
     L.ppb_plan_host_chunks.restype = i64
     L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]

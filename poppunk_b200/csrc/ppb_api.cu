@@ -88,14 +88,9 @@ struct TileList {
 std::mutex g_tile_mu;
 std::map<TileKey, TileList> g_tiles;
 
-int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
-    std::lock_guard<std::mutex> lk(g_tile_mu);
-    auto it = g_tiles.find(key);
-    if (it != g_tiles.end()) {
-        *out = it->second;
-        return PPB_OK;
-    }
-    std::vector<int2> v;
+static_assert(ppb::kTI == PPB_TILE_ROWS, "include/ppb.h documents the row-tile height");
+// the (row tile, column tile) list of one launch, in execution order (host only: also behind ppb_plan_tiles)
+void plan_tiles(const TileKey &key, std::vector<int2> *v) {
     const int64_t nTi = (key.nA + ppb::kTI - 1) / ppb::kTI, nTj = (key.nB + key.tj - 1) / key.tj;
     const int64_t it_lo = key.i_lo / ppb::kTI, it_hi = key.i_hi / ppb::kTI;
     const int64_t kBand = std::max(1, key.band);
@@ -104,9 +99,20 @@ int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
         for (int64_t jt = 0; jt < nTj; jt++)
             for (int64_t ti = std::max(b0, it_lo); ti < b1; ti++) {
                 if (key.self && jt * key.tj + key.tj - 1 <= ti * ppb::kTI) continue;  // no j > i in this tile
-                v.push_back(make_int2((int)ti, (int)jt));
+                v->push_back(make_int2((int)ti, (int)jt));
             }
     }
+}
+
+int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
+    std::lock_guard<std::mutex> lk(g_tile_mu);
+    auto it = g_tiles.find(key);
+    if (it != g_tiles.end()) {
+        *out = it->second;
+        return PPB_OK;
+    }
+    std::vector<int2> v;
+    plan_tiles(key, &v);
     TileList tl;
     tl.n = (int64_t)v.size();
     if (tl.n) {
@@ -1187,6 +1193,24 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int6
     }
     if (n_degenerate) *n_degenerate = (int64_t)deg;
     return PPB_OK;
+}
+
+int64_t ppb_plan_tiles(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end, int32_t tile_cols,
+                       int32_t band_tiles, int32_t *tiles, int64_t max_tiles) {
+    const int64_t total_rows = ppb_num_rows(n_ref, n_qry, self);
+    if (n_ref < 1 || (!self && n_qry < 1) || row_begin < 0 || row_end > total_rows || row_begin >= row_end || tile_cols < 1 ||
+        band_tiles < 1)
+        return -1;
+    TileKey key{0, self ? n_ref : n_qry, n_ref, self, tile_cols, 0, 0, band_tiles};
+    key.i_lo = self ? row_idx(row_begin, n_ref) : row_begin / n_ref;   // the same row-genome range ppb_query_dev derives
+    key.i_hi = self ? row_idx(row_end - 1, n_ref) : (row_end - 1) / n_ref;
+    std::vector<int2> v;
+    plan_tiles(key, &v);
+    for (size_t t = 0; t < v.size() && (int64_t)t < max_tiles && tiles; t++) {
+        tiles[2 * t] = v[t].x;
+        tiles[2 * t + 1] = v[t].y;
+    }
+    return (int64_t)v.size();
 }
 
 int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,

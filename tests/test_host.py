@@ -244,3 +244,38 @@ def test_reference_arm_under_torchrun_uses_all_cores():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
     assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+@pytest.mark.parametrize("n_ref,n_qry,self_mode,tile_cols,band", [(300, 0, True, 128, 2), (130, 0, True, 128, 64),
+                                                                  (200, 0, True, 32, 3), (257, 150, False, 128, 2),
+                                                                  (65, 1, False, 64, 1), (2, 0, True, 128, 4)])
+def test_tile_schedule_covers_every_pair_once(lib, n_ref, n_qry, self_mode, tile_cols, band):
+    """The launch plan of the distance kernel (ppb_plan_tiles, the list ppb_query_dev uploads): for the whole job and
+    for shards that start/end inside row tiles, every (i, j) pair of the shard lies in exactly one listed tile, no tile
+    is listed twice, and self mode lists no tile without a j > i."""
+    total = lib.ppb_num_rows(n_ref, n_qry, int(self_mode))
+    n_rows_side = n_ref if self_mode else n_qry
+    for b, e in [(0, total), (total // 3, total - total // 5), (total // 2, total // 2 + 1)]:
+        if b >= e:
+            continue
+        n = lib.ppb_plan_tiles(n_ref, n_qry, int(self_mode), b, e, tile_cols, band, None, 0)
+        assert n > 0
+        tiles = np.zeros((n, 2), dtype=np.int32)
+        assert lib.ppb_plan_tiles(n_ref, n_qry, int(self_mode), b, e, tile_cols, band, tiles.ctypes.data, n) == n
+        assert len({(int(t), int(c)) for t, c in tiles}) == n                         # no duplicates
+        listed = {(int(t), int(c)) for t, c in tiles}
+        rows = np.arange(b, e, max(1, (e - b) // 4000))                                # sample of the shard's rows
+        rows = np.unique(np.concatenate([rows, [b, e - 1]]))
+        for r in rows:
+            if self_mode:
+                i = lib.ppb_calc_row_idx(int(r), n_ref)
+                j = lib.ppb_calc_col_idx(int(r), i, n_ref)
+            else:
+                i, j = int(r) // n_ref, int(r) % n_ref
+            assert 0 <= i < n_rows_side and (i // 64, j // tile_cols) in listed, (r, i, j)
+        if self_mode:                                                                  # every listed tile holds some j > i
+            assert all((c + 1) * tile_cols - 1 > t * 64 for t, c in tiles)
+        i_lo = lib.ppb_calc_row_idx(b, n_ref) if self_mode else b // n_ref
+        i_hi = lib.ppb_calc_row_idx(e - 1, n_ref) if self_mode else (e - 1) // n_ref
+        assert tiles[:, 0].min() == i_lo // 64 and tiles[:, 0].max() == i_hi // 64     # no row tile outside the shard
+    assert lib.ppb_plan_tiles(n_ref, n_qry, int(self_mode), 0, total + 1, tile_cols, band, None, 0) == -1
