@@ -1,4 +1,8 @@
-"""The HDF5 branch of the sketch-database reader, against the reference's OWN writer.
+"""Seams with the reference, exercised with the reference's OWN Python code on both sides (CPU, no GPU):
+(1) the HDF5 branch of the sketch-database reader against the reference's writer; (2) the queryDatabase wrapper against the
+reference's wrapper.
+
+(1) The HDF5 branch of the sketch-database reader, against the reference's OWN writer.
 
 h5py / libhdf5 are not in the image, so the file format itself cannot be exercised; what can be pinned is the object
 schema: PopPUNK/web.py:14-61 ``sketch_to_hdf5`` (the reference's JSON -> HDF5 converter) is extracted from the reference
@@ -105,3 +109,60 @@ def test_read_db_reads_what_the_reference_writer_writes(tmp_path, monkeypatch, g
     assert sketchlib.getSeqsInDb(prefix) == ["sampleA", "sampleB"]
     sub = sketchlib.read_db(prefix, ["sampleB"])
     assert sub.names == ["sampleB"] and sub.sketches.shape[0] == 1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+def test_wrapper_forwards_like_the_reference_wrapper(monkeypatch, capsys):
+    """PopPUNK/sketchlib.py:475-632 ``queryDatabase`` (extracted from the reference tree, its ``pp_sketchlib`` replaced by
+    a recorder) and ``poppunk_b200.sketchlib.queryDatabase`` (its native entry replaced by the same recorder) must hand
+    the native layer the same ten arguments, pass its result through untouched and fail the same way."""
+    from poppunk_b200 import sketchlib
+    tree = ast.parse(open(os.path.join(REF, "PopPUNK", "sketchlib.py")).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "queryDatabase")
+    calls = []
+    NAMES = ["ref_db_name", "query_db_name", "rList", "qList", "klist", "random_correct", "jaccard", "num_threads",
+             "use_gpu", "device_id"]
+    sentinel = np.arange(6, dtype=np.float32).reshape(3, 2)
+
+    def recorder(*args, **kwargs):
+        rec = dict(zip(NAMES, args))
+        rec.update(kwargs)
+        rec["klist"] = [int(k) for k in rec["klist"]]
+        calls.append(rec)
+        return sentinel
+
+    class FakeNative:
+        queryDatabase = staticmethod(recorder)
+
+    env = {"pp_sketchlib": FakeNative, "os": os, "sys": sys, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "sketchlib.py", "exec"), env)
+    ref_query = env["queryDatabase"]
+    monkeypatch.setattr(sketchlib, "pp_queryDatabase", recorder)
+    klist = np.array([13, 17, 21, 25, 29])
+    r, q = ["a", "b", "c"], ["x", "y"]
+    cases = [dict(rNames=r, qNames=r, dbPrefix="some/db", queryPrefix="some/db", klist=klist, self=True, threads=4,
+                  use_gpu=True, deviceid=1),
+             dict(rNames=r, qNames=q, dbPrefix="some/db", queryPrefix="other/qdb", klist=klist, self=False, threads=2,
+                  use_gpu=False, deviceid=0)]
+    for kw in cases:
+        calls.clear()
+        out_ref = ref_query(**kw)
+        out_mine = sketchlib.queryDatabase(**kw)
+        assert len(calls) == 2 and calls[0] == calls[1], calls
+        assert out_ref is sentinel and out_mine is sentinel
+    # self query across two prefixes: the same exception type and text
+    errs = []
+    for f in (ref_query, sketchlib.queryDatabase):
+        with pytest.raises(RuntimeError) as ei:
+            f(r, r, "some/db", "other/db", klist, self=True)
+        errs.append(str(ei.value))
+    assert errs[0] == errs[1] == "Must use same db for self query"
+    # query names that are also reference names: exit status 1 and the same three lines on stderr
+    texts = []
+    for f in (ref_query, sketchlib.queryDatabase):
+        capsys.readouterr()
+        with pytest.raises(SystemExit) as ei:
+            f(r, ["b", "z"], "some/db", "other/qdb", klist, self=False)
+        assert ei.value.code == 1
+        texts.append(capsys.readouterr().err)
+    assert texts[0] == texts[1] and "Unique names are required!" in texts[0]
