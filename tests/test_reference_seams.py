@@ -166,3 +166,26 @@ def test_wrapper_forwards_like_the_reference_wrapper(monkeypatch, capsys):
         assert ei.value.code == 1
         texts.append(capsys.readouterr().err)
     assert texts[0] == texts[1] and "Unique names are required!" in texts[0]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+def test_refine_module_has_the_bound_functions_and_argument_names():
+    """src/python_bindings.cpp:79-136 binds nine functions with named arguments (py::arg); PopPUNK calls several of them
+    by keyword (network.py:1087-1089, 1180-1184; models.py:1216-1222; assign.py:681-686).  poppunk_b200.refine must offer
+    every one of them with the same argument names in the same order (extra trailing arguments of its own are allowed)."""
+    import inspect
+    import re
+    from poppunk_b200 import refine
+    src = open(os.path.join(REF, "src", "python_bindings.cpp")).read()
+    blocks = re.split(r'm\.def\(\s*"', src)[1:]
+    bound = {}
+    for b in blocks:
+        name = b.split('"', 1)[0]
+        body = b.split("m.def(", 1)[0]
+        bound[name] = re.findall(r'py::arg\("(\w+)"\)', body)
+    assert set(bound) == {"assignThreshold", "edgeThreshold", "generateTuples", "generateAllTuples", "thresholdIterate1D",
+                          "thresholdIterate2D", "extend", "lowerRank", "get_kNN_distances"}
+    for name, args in bound.items():
+        assert hasattr(refine, name), name
+        mine = list(inspect.signature(getattr(refine, name)).parameters)
+        assert mine[:len(args)] == args, (name, args, mine)
