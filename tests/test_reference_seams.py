@@ -189,3 +189,44 @@ def test_refine_module_has_the_bound_functions_and_argument_names():
         assert hasattr(refine, name), name
         mine = list(inspect.signature(getattr(refine, name)).parameters)
         assert mine[:len(args)] == args, (name, args, mine)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+def test_every_reference_call_site_binds_to_the_replacement():
+    """Walk every ``pp_sketchlib.<f>(...)`` / ``poppunk_refine.<f>(...)`` call in the reference package (for the functions
+    this engine replaces) and bind its positional count and keyword names against the replacement's signature: a
+    maintainer who swaps the imports must not hit a TypeError anywhere."""
+    import glob
+    import inspect
+    from poppunk_b200 import refine, reshape, sketchlib
+    targets = {("pp_sketchlib", "queryDatabase"): sketchlib.pp_queryDatabase,
+               ("pp_sketchlib", "longToSquare"): reshape.longToSquare,
+               ("pp_sketchlib", "squareToLong"): reshape.squareToLong,
+               ("pp_sketchlib", "longToSquareMulti"): reshape.longToSquareMulti}
+    for name in ("assignThreshold", "edgeThreshold", "generateTuples", "generateAllTuples", "thresholdIterate1D",
+                 "thresholdIterate2D", "extend", "lowerRank", "get_kNN_distances"):
+        targets[("poppunk_refine", name)] = getattr(refine, name)
+    seen = {k: 0 for k in targets}
+    files = glob.glob(os.path.join(REF, "PopPUNK", "*.py")) + glob.glob(os.path.join(REF, "scripts", "*.py")) + \
+        glob.glob(os.path.join(REF, "test", "*.py"))
+    import warnings
+    for path in files:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # the reference's own string-escape warnings
+            tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name):
+                key = (node.func.value.id, node.func.attr)
+                if key not in targets:
+                    continue
+                sig = inspect.signature(targets[key])
+                args = [None] * len(node.args)
+                kwargs = {kw.arg: None for kw in node.keywords if kw.arg is not None}
+                try:
+                    sig.bind(*args, **kwargs)
+                except TypeError as e:
+                    raise AssertionError(f"{os.path.relpath(path, REF)}:{node.lineno} {key[0]}.{key[1]}: {e}") from None
+                seen[key] += 1
+    # every replaced function is actually called somewhere in the reference (so the check above is not vacuous)
+    assert all(v > 0 for v in seen.values()), {k: v for k, v in seen.items() if v == 0}
+    assert seen[("pp_sketchlib", "queryDatabase")] >= 10
