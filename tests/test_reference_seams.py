@@ -230,3 +230,31 @@ def test_every_reference_call_site_binds_to_the_replacement():
     # every replaced function is actually called somewhere in the reference (so the check above is not vacuous)
     assert all(v > 0 for v in seen.values()), {k: v for k, v in seen.items() if v == 0}
     assert seen[("pp_sketchlib", "queryDatabase")] >= 10
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+def test_distfiles_interoperate_with_the_reference_functions(tmp_path):
+    """poppunk_b200.distfiles against PopPUNK/utils.py:135-261 themselves (extracted): each side reads what the other
+    writes, and the row <-> pair generators agree element for element."""
+    import pickle
+    from poppunk_b200 import distfiles
+    tree = ast.parse(open(os.path.join(REF, "PopPUNK", "utils.py")).read())
+    env = {"pickle": pickle, "np": np, "sys": sys}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("storePickle", "readPickle", "iterDistRows", "listDistInts"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "utils.py", "exec"), env)
+    names = [f"g{i}" for i in range(11)]
+    X = np.random.default_rng(0).random((55, 2)).astype(np.float32)
+    a, b = str(tmp_path / "mine.dists"), str(tmp_path / "theirs.dists")
+    distfiles.storePickle(names, names, True, X, a)
+    env["storePickle"](names, names, True, X, b)
+    for reader in (distfiles.readPickle, env["readPickle"]):
+        for prefix in (a, b):
+            r, q, s, Y = reader(prefix, enforce_self=True)
+            assert (r, q, s) == (names, names, True) and Y.dtype == np.float32 and (Y == X).all()
+    for self_mode, rr, qq in ((True, names, names), (False, names[:4], names[4:])):
+        assert list(distfiles.iterDistRows(rr, qq, self_mode)) == list(env["iterDistRows"](rr, qq, self_mode))
+        assert list(distfiles.listDistInts(rr, qq, self_mode)) == list(env["listDistInts"](rr, qq, self_mode))
+    for f in (distfiles.iterDistRows, env["iterDistRows"]):
+        with pytest.raises(RuntimeError):
+            list(f(names, names[:3], True))
