@@ -43,8 +43,11 @@ class FakeGroup:
     def keys(self):
         return sorted(self.children)          # h5py iterates names alphabetically (PopPUNK/sketchlib.py:211)
 
-    def __getitem__(self, name):
-        return self.children[name]
+    def __getitem__(self, name):            # h5py accepts 'group/child' paths
+        node = self
+        for part in name.split("/"):
+            node = node.children[part]
+        return node
 
     def __contains__(self, name):
         return name in self.children
@@ -258,3 +261,31 @@ def test_distfiles_interoperate_with_the_reference_functions(tmp_path):
     for f in (distfiles.iterDistRows, env["iterDistRows"]):
         with pytest.raises(RuntimeError):
             list(f(names, names[:3], True))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+def test_db_parameter_readers_agree_with_the_reference_readers(tmp_path, monkeypatch):
+    """PopPUNK/sketchlib.py:109-214 getSketchSize / getKmersFromReferenceDatabase / readDBParams / getSeqsInDb
+    (extracted, on the stand-in h5py) and their poppunk_b200.sketchlib namesakes return the same values for a database
+    written by the reference's own writer."""
+    from poppunk_b200 import sketchlib
+    fake = FakeH5py()
+    web = ast.parse(open(os.path.join(REF, "PopPUNK", "web.py")).read())
+    env = {"h5py": fake, "os": os, "sys": sys, "np": np, "json": json}
+    exec(compile(ast.Module(body=[n for n in web.body if isinstance(n, ast.FunctionDef) and n.name == "sketch_to_hdf5"],
+                            type_ignores=[]), "web.py", "exec"), env)
+    sk = ast.parse(open(os.path.join(REF, "PopPUNK", "sketchlib.py")).read())
+    wanted = ("getSketchSize", "getKmersFromReferenceDatabase", "readDBParams", "getSeqsInDb")
+    exec(compile(ast.Module(body=[n for n in sk.body if isinstance(n, ast.FunctionDef) and n.name in wanted],
+                            type_ignores=[]), "sketchlib.py", "exec"), env)
+    prefix = str(tmp_path / "db")
+    os.makedirs(prefix)
+    sketch_json = open(os.path.join(REF, "test", "json_sketch.txt")).read()
+    env["sketch_to_hdf5"]({"s2": sketch_json, "s1": sketch_json, "s3": sketch_json}, prefix)
+    monkeypatch.setattr(sketchlib, "h5py", fake)
+    assert sketchlib.getSketchSize(prefix) == env["getSketchSize"](prefix) == (156, False)
+    assert (sketchlib.getKmersFromReferenceDatabase(prefix) == env["getKmersFromReferenceDatabase"](prefix)).all()
+    mine, theirs = sketchlib.readDBParams(prefix), env["readDBParams"](prefix)
+    assert (mine[0] == theirs[0]).all() and mine[1:] == theirs[1:]
+    h5_file = os.path.join(prefix, "db.h5")
+    assert sketchlib.getSeqsInDb(h5_file) == env["getSeqsInDb"](h5_file) == ["s1", "s2", "s3"]
