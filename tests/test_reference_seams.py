@@ -289,3 +289,37 @@ def test_db_parameter_readers_agree_with_the_reference_readers(tmp_path, monkeyp
     assert (mine[0] == theirs[0]).all() and mine[1:] == theirs[1:]
     h5_file = os.path.join(prefix, "db.h5")
     assert sketchlib.getSeqsInDb(h5_file) == env["getSeqsInDb"](h5_file) == ["s1", "s2", "s3"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
+@pytest.mark.parametrize("backend", ["reference_build", "restatement"])
+def test_reference_test_refine_script_passes(oracle, backend):
+    """test/test-refine.py — the reference's OWN test of poppunk_refine — executed as is, with ``poppunk_refine`` bound to
+    (a) the reference's sources compiled into oracle/_ref (so that build is held to the reference's own test) and
+    (b) the oracle's C restatement.  The script raises RuntimeError on any mismatch."""
+    import types
+    if backend == "reference_build":
+        if not oracle.ref_available():
+            pytest.skip("oracle/_ref not built")
+        impl = oracle.ref
+    else:
+        impl = oracle
+    tup = lambda ij: list(zip(ij[0].tolist(), ij[1].tolist()))
+    lists = lambda t: tuple(a.tolist() for a in t)
+    mod = types.ModuleType("poppunk_refine")
+    mod.assignThreshold = lambda d, slope, xm, ym, threads=1: impl.assign_threshold(d, slope, xm, ym)
+    mod.generateTuples = lambda a, within, self=True, num_ref=0, int_offset=0: tup(impl.generate_tuples(a, within, self, num_ref, int_offset))
+    mod.edgeThreshold = lambda d, slope, xm, ym: tup(impl.edge_iterate(d, slope, xm, ym))
+    mod.thresholdIterate1D = lambda d, offs, slope, x0, y0, x1, y1, threads=1: lists(impl.threshold_iterate_1d(d, offs, slope, x0, y0, x1, y1))
+    mod.thresholdIterate2D = lambda d, xm, ym: lists(impl.threshold_iterate_2d(d, xm, ym))
+    saved = sys.modules.get("poppunk_refine")
+    sys.modules["poppunk_refine"] = mod
+    try:
+        np.random.seed(12345)        # the script draws its cloud unseeded; fix it so the run is reproducible
+        src = open(os.path.join(REF, "test", "test-refine.py")).read()
+        exec(compile(src, "test-refine.py", "exec"), {"__name__": "__main__"})
+    finally:
+        if saved is None:
+            del sys.modules["poppunk_refine"]
+        else:
+            sys.modules["poppunk_refine"] = saved
