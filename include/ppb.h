@@ -92,6 +92,14 @@ size_t ppb_packed_bytes(int64_t n, int32_t K, int32_t sketchsize64);
 int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, int64_t n,
                  int32_t K, int32_t sketchsize64, uint32_t *d_packed, void *stream);
 
+/* The same for a PART of the genomes, written to several packed arrays at once: genomes [g_begin, g_end) of the
+ * n-genome layout (g_end may run into the padding, i.e. up to n rounded up to 128) are read from d_sketch_part
+ * (row g - g_begin, or d_idx[g - g_begin]) and stored into each of the n_dst packed arrays d_packed[0..n_dst) —
+ * this device's and, in a single-process multi-GPU call, the peers' (NVLink peer-mapped) — so every device uploads
+ * and packs 1/G of the sketches instead of all of them.                                                        */
+int ppb_pack_part_dev(const uint64_t *d_sketch_part, const int64_t *d_idx, int64_t g_begin, int64_t g_end, int64_t n,
+                      int32_t K, int32_t sketchsize64, uint32_t *const *d_packed, int32_t n_dst, void *stream);
+
 /* The hot path.  Replaces pp_sketchlib.queryDatabase(...) after the sketches are on the device.
  *   d_qry_packed == NULL  => self mode (n_qry ignored)
  *   kmers        host int32 [K], ascending k-mer lengths (x of the regression)
@@ -231,6 +239,36 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref,
                    int32_t out_mode, void *out,
                    const ppb_boundary *boundary, int8_t *labels,
                    int64_t *n_degenerate, int32_t device_id);
+
+/* The same call on SEVERAL devices of one process — what the drop-in queryDatabase() uses (PopPUNK is one process:
+ * PopPUNK/utils.py:118-126, __main__.py:220): the row range is cut into n_devices contiguous shards of equal pair
+ * count on row-tile boundaries (ppb_plan_device_shards), one worker thread per device uploads and packs 1/G of the
+ * reference sketches into every device's packed array (peer stores over NVLink; without peer access every device
+ * uploads all of them), uploads only ITS OWN queries in non-self mode (rows are query-major), runs its shard in row
+ * chunks and copies them back straight into the ONE caller buffer.  No exchange between devices.  A job with fewer
+ * than ~16 Mi rows per device uses fewer devices.  ppb_query_host(…, device_id) is this call with one device.   */
+int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref,
+                         const uint64_t *qry, int64_t n_qry,
+                         const int32_t *kmers, int32_t K, int32_t sketchsize64, int32_t bbits,
+                         const float *rand_table, int32_t n_clusters,
+                         const uint16_t *ref_cluster, const uint16_t *qry_cluster,
+                         int64_t row_begin, int64_t row_end,
+                         int32_t out_mode, void *out,
+                         const ppb_boundary *boundary, int8_t *labels,
+                         int64_t *n_degenerate, const int32_t *device_ids, int32_t n_devices);
+/* The n_devices+1 row boundaries ppb_query_host_multi uses (cuts[g] .. cuts[g+1] is device g's shard). Host-only. */
+int64_t ppb_plan_device_shards(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end,
+                               int32_t n_devices, int64_t *cuts);
+
+/* Host memory for results the LIBRARY's caller hands on as its own (the drop-in returns a NumPy array it owns):
+ * ppb_host_alloc returns a block of at least `bytes` (anonymous mapping, transparent huge pages requested) from a
+ * small pool; ppb_host_free hands it back.  A block that is reused has been touched and is page-locked
+ * (cudaHostRegister) on that first reuse, so from the second call of a process on results are DMA-ed straight into
+ * the array the caller receives.  PPB_HOST_PIN=0 disables the page-locking; PPB_HOST_POOL_MAX_GB bounds the idle
+ * bytes kept (default: half of physical memory); ppb_release_workspace() drops idle blocks.                    */
+void *ppb_host_alloc(size_t bytes);
+int   ppb_host_free(void *p);
+int   ppb_host_pool_stats(size_t *bytes_held, size_t *bytes_in_use, size_t *bytes_pinned);
 
 /* How ppb_query_host cuts [row_begin,row_end) into launches: chunks of at most cap_rows rows that end on row-tile
  * boundaries (64 genomes of the row side) whenever a whole row tile fits.  Writes up to max_chunks (begin,end)

@@ -21,7 +21,8 @@ SYMBOLS = [
     "ppb_edges_scratch_bytes", "ppb_edges_from_dists_dev", "ppb_edges_from_labels_dev", "ppb_long_to_square_dev",
     "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev", "ppb_plan_host_chunks",
     "ppb_generate_all_tuples_dev", "ppb_threshold_iterate_1d_dev", "ppb_threshold_iterate_2d_dev", "ppb_knn_dev",
-    "ppb_lower_rank_dev", "ppb_extend_dev", "ppb_plan_tiles",
+    "ppb_lower_rank_dev", "ppb_extend_dev", "ppb_plan_tiles", "ppb_pack_part_dev", "ppb_query_host_multi",
+    "ppb_plan_device_shards", "ppb_host_alloc", "ppb_host_free", "ppb_host_pool_stats",
 ]
 
 
@@ -73,6 +74,18 @@ def load():
     L.ppb_query_host.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp,
                                  vp, i32]
     L.ppb_query_host.restype = C.c_int
+    L.ppb_query_host_multi.argtypes = L.ppb_query_host.argtypes[:-1] + [vp, i32]
+    L.ppb_query_host_multi.restype = C.c_int
+    L.ppb_plan_device_shards.argtypes = [i64, i64, i32, i64, i64, i32, vp]
+    L.ppb_plan_device_shards.restype = i64
+    L.ppb_pack_part_dev.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp, i32, vp]
+    L.ppb_pack_part_dev.restype = C.c_int
+    L.ppb_host_alloc.argtypes = [C.c_size_t]
+    L.ppb_host_alloc.restype = vp
+    L.ppb_host_free.argtypes = [vp]
+    L.ppb_host_free.restype = C.c_int
+    L.ppb_host_pool_stats.argtypes = [vp, vp, vp]
+    L.ppb_host_pool_stats.restype = C.c_int
     L.ppb_assign_threshold_host.argtypes = [vp, i64, i32, f32, f32, vp, i32]
     L.ppb_assign_threshold_host.restype = C.c_int
     L.ppb_release_workspace.restype = C.c_int

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -208,19 +209,35 @@ size_t ppb_packed_bytes(int64_t n, int32_t K, int32_t sketchsize64) {
     return (size_t)K * n_slices_of(sketchsize64) * round_up(std::max<int64_t>(n, 1), ppb::kPad) * ppb::kSliceBytes;
 }
 
+int ppb_pack_part_dev(const uint64_t *d_sketch_part, const int64_t *d_idx, int64_t g_begin, int64_t g_end, int64_t n,
+                      int32_t K, int32_t sketchsize64, uint32_t *const *d_packed, int32_t n_dst, void *stream) {
+    const int64_t n_pad = round_up(std::max<int64_t>(n, 1), ppb::kPad);
+    if (!d_packed || n_dst < 1 || n_dst > PPB_MAX_PEERS || n < 0 || K < 1 || K > PPB_MAX_K || sketchsize64 < 1 ||
+        g_begin < 0 || g_end < g_begin || g_end > n_pad || (!d_sketch_part && g_begin < std::min(g_end, n)))
+        return fail(PPB_ERR_ARG, "ppb_pack_part_dev: bad argument");
+    if (g_begin == g_end) return PPB_OK;
+    ppb::PackDsts dsts;
+    dsts.n = n_dst;
+    for (int d = 0; d < n_dst; d++) {
+        if (!d_packed[d]) return fail(PPB_ERR_ARG, "ppb_pack_part_dev: null destination");
+        dsts.p[d] = d_packed[d];
+    }
+    const int64_t units = (int64_t)K * n_slices_of(sketchsize64) * (g_end - g_begin);  // one warp per 1792-byte unit
+    const int64_t blocks = std::min<int64_t>((units + ppb::kPackWarps - 1) / ppb::kPackWarps, 148 * 32);
+    ppb::pack_kernel<<<(unsigned)blocks, ppb::kPackWarps * 32, 0, (cudaStream_t)stream>>>(
+        d_sketch_part, d_idx, g_begin, g_end, n, n_pad, K, sketchsize64, n_slices_of(sketchsize64), dsts);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
+
 int ppb_pack_dev(const uint64_t *d_sketch, int64_t n_src, const int64_t *d_idx, int64_t n, int32_t K,
                  int32_t sketchsize64, uint32_t *d_packed, void *stream) {
     if (!d_sketch || !d_packed || n < 0 || K < 1 || K > PPB_MAX_K || sketchsize64 < 1)
         return fail(PPB_ERR_ARG, "ppb_pack_dev: bad argument");
     if (!d_idx && n != n_src) return fail(PPB_ERR_ARG, "ppb_pack_dev: n != n_src without an index list");
     const int64_t n_pad = round_up(std::max<int64_t>(n, 1), ppb::kPad);
-    const int64_t units = (int64_t)K * n_slices_of(sketchsize64) * n_pad;  // one warp per 1792-byte unit
-    const int64_t blocks = std::min<int64_t>((units + ppb::kPackWarps - 1) / ppb::kPackWarps, 148 * 32);
-    ppb::pack_kernel<<<(unsigned)blocks, ppb::kPackWarps * 32, 0, (cudaStream_t)stream>>>(
-        d_sketch, d_idx, n, n_pad, K, sketchsize64, n_slices_of(sketchsize64), d_packed);
-    g_launches++;
-    PPB_CUDA(cudaGetLastError());
-    return PPB_OK;
+    return ppb_pack_part_dev(d_sketch, d_idx, 0, n_pad, n, K, sketchsize64, &d_packed, 1, stream);
 }
 
 static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uint32_t *d_qry_packed, int64_t n_qry,
@@ -850,8 +867,9 @@ int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *l
 }
 
 // ------------------------------------------------------------------------------------------------
-// Host-buffer path: H2D, pack, row-chunked kernel launches, D2H overlapped on a second stream.
+// Host-buffer path: see ppb_host.inl (included below)
 // ------------------------------------------------------------------------------------------------
+extern "C++" {
 namespace {
 struct DevBuf {
     void *p = nullptr;
@@ -867,333 +885,8 @@ struct DevBuf {
         return PPB_OK;
     }
 };
-// Grow-only device workspace reused by successive host-buffer calls on the same device (cudaMalloc/cudaFree of
-// multi-GB buffers per call would otherwise show up in the end-to-end time).  Host calls on one device are
-// serialised by the slot mutex; ppb_release_workspace() returns the memory.
-struct Workspace {
-    std::mutex mu;
-    std::map<std::pair<int, int>, std::pair<void *, size_t>> slots;  // (device, slot) -> (ptr, capacity)
-    int get(int dev, int slot, size_t bytes, void **out) {
-        auto &e = slots[{dev, slot}];
-        if (e.second < bytes || !e.first) {
-            if (e.first) cudaFree(e.first);
-            e.first = nullptr;
-            e.second = 0;
-            if (cudaMalloc(&e.first, std::max<size_t>(bytes, 256)) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(PPB_ERR_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
-            }
-            e.second = std::max<size_t>(bytes, 256);
-        }
-        *out = e.first;
-        return PPB_OK;
-    }
-    // pinned host staging buffers (results bound for PAGEABLE caller memory), same grow-only policy
-    std::map<std::pair<int, int>, std::pair<void *, size_t>> pinned;
-    int get_pinned(int dev, int slot, size_t bytes, void **out) {
-        auto &e = pinned[{dev, slot}];
-        if (e.second < bytes || !e.first) {
-            if (e.first) cudaFreeHost(e.first);
-            e.first = nullptr;
-            e.second = 0;
-            if (cudaHostAlloc(&e.first, std::max<size_t>(bytes, 256), cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(PPB_ERR_NOMEM, "cudaHostAlloc failed for " + std::to_string(bytes) + " bytes");
-            }
-            e.second = std::max<size_t>(bytes, 256);
-        }
-        *out = e.first;
-        return PPB_OK;
-    }
-    void release() {
-        for (auto &kv : slots)
-            if (kv.second.first) cudaFree(kv.second.first);
-        slots.clear();
-        for (auto &kv : pinned)
-            if (kv.second.first) cudaFreeHost(kv.second.first);
-        pinned.clear();
-    }
-};
-Workspace g_ws;
-constexpr size_t kHostRing = 8;  // result buffers of the host-buffer path (chunks in flight between kernel and D2H)
-enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
-
-// true when the CUDA driver can DMA straight into p (pinned / registered / managed host memory)
-bool is_dma_able(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
-// memcpy split over a few threads: one core cannot take 50 GB/s out of a staging buffer into fresh pages
-void parallel_memcpy(void *dst, const void *src, size_t bytes, int threads) {
-    if (threads <= 1 || bytes < ((size_t)8 << 20)) {
-        std::memcpy(dst, src, bytes);
-        return;
-    }
-    const size_t piece = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; t++) {
-        const size_t off = (size_t)t * piece;
-        if (off >= bytes) break;
-        pool.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, std::min(piece, bytes - off)); });
-    }
-    std::memcpy(dst, src, std::min(piece, bytes));
-    for (auto &th : pool) th.join();
-}
-
-struct Stream {
-    cudaStream_t s = nullptr;
-    ~Stream() {
-        if (s) cudaStreamDestroy(s);
-    }
-};
-struct Event {
-    cudaEvent_t e = nullptr;
-    ~Event() {
-        if (e) cudaEventDestroy(e);
-    }
-};
 }  // namespace
-
-int ppb_query_host(const uint64_t *ref, int64_t n_ref, const uint64_t *qry, int64_t n_qry, const int32_t *kmers,
-                   int32_t K, int32_t sketchsize64, int32_t bbits, const float *rand_table, int32_t n_clusters,
-                   const uint16_t *ref_cluster, const uint16_t *qry_cluster, int64_t row_begin, int64_t row_end,
-                   int32_t out_mode, void *out, const ppb_boundary *boundary, int8_t *labels,
-                   int64_t *n_degenerate, int32_t device_id) {
-    if (bbits != PPB_BBITS) return fail(PPB_ERR_ARG, "ppb_query_host: bbits must be 14");
-    if (!ref || !kmers || K < 1 || K > PPB_MAX_K || sketchsize64 < 1 || n_ref < 0)
-        return fail(PPB_ERR_ARG, "ppb_query_host: bad argument");
-    const int self = qry == nullptr;
-    const int64_t total_rows = ppb_num_rows(n_ref, n_qry, self);
-    if (row_begin < 0 || row_end > total_rows || row_begin > row_end)
-        return fail(PPB_ERR_ARG, "ppb_query_host: bad row range");
-    if (n_degenerate) *n_degenerate = 0;
-    if (row_begin == row_end) return PPB_OK;
-    int ndev = ppb_device_count();
-    if (ndev <= 0) return fail(PPB_ERR_NO_DEVICE, "ppb_query_host: no CUDA device (this engine has no CPU path)");
-    if (device_id < 0 || device_id >= ndev) return fail(PPB_ERR_ARG, "ppb_query_host: bad device id");
-    PPB_CUDA(cudaSetDevice(device_id));
-
-    Stream s_compute, s_copy;
-    PPB_CUDA(cudaStreamCreateWithFlags(&s_compute.s, cudaStreamNonBlocking));
-    PPB_CUDA(cudaStreamCreateWithFlags(&s_copy.s, cudaStreamNonBlocking));
-
-    std::lock_guard<std::mutex> ws_lock(g_ws.mu);  // one host call at a time shares the device workspace
-    auto ws = [&](int slot, size_t bytes, void **ptr) { return g_ws.get(device_id, slot, bytes, ptr); };
-
-    const int64_t W = (int64_t)sketchsize64 * PPB_BBITS;
-    const size_t ref_bytes = (size_t)n_ref * K * W * 8, qry_bytes = self ? 0 : (size_t)n_qry * K * W * 8;
-    void *d_ref_raw = nullptr, *d_qry_raw = nullptr, *d_ref = nullptr, *d_qry = nullptr, *d_tab = nullptr,
-         *d_rc = nullptr, *d_qc = nullptr, *d_deg = nullptr;
-    if (int rc = ws(WS_REF_RAW, ref_bytes, &d_ref_raw)) return rc;
-    if (int rc = ws(WS_REF, ppb_packed_bytes(n_ref, K, sketchsize64), &d_ref)) return rc;
-    PPB_CUDA(cudaMemcpyAsync(d_ref_raw, ref, ref_bytes, cudaMemcpyHostToDevice, s_compute.s));
-    if (int rc = ppb_pack_dev((const uint64_t *)d_ref_raw, n_ref, nullptr, n_ref, K, sketchsize64, (uint32_t *)d_ref,
-                              s_compute.s))
-        return rc;
-    if (!self) {
-        if (int rc = ws(WS_QRY_RAW, qry_bytes, &d_qry_raw)) return rc;
-        if (int rc = ws(WS_QRY, ppb_packed_bytes(n_qry, K, sketchsize64), &d_qry)) return rc;
-        PPB_CUDA(cudaMemcpyAsync(d_qry_raw, qry, qry_bytes, cudaMemcpyHostToDevice, s_compute.s));
-        if (int rc = ppb_pack_dev((const uint64_t *)d_qry_raw, n_qry, nullptr, n_qry, K, sketchsize64,
-                                  (uint32_t *)d_qry, s_compute.s))
-            return rc;
-    }
-    if (rand_table) {
-        if (n_clusters < 1 || !ref_cluster || (!self && !qry_cluster))
-            return fail(PPB_ERR_ARG, "ppb_query_host: random table without cluster ids");
-        const size_t tb = (size_t)n_clusters * n_clusters * K * sizeof(float);
-        if (int rc = ws(WS_TAB, tb, &d_tab)) return rc;
-        if (int rc = ws(WS_RC, (size_t)n_ref * 2, &d_rc)) return rc;
-        PPB_CUDA(cudaMemcpyAsync(d_tab, rand_table, tb, cudaMemcpyHostToDevice, s_compute.s));
-        PPB_CUDA(cudaMemcpyAsync(d_rc, ref_cluster, (size_t)n_ref * 2, cudaMemcpyHostToDevice, s_compute.s));
-        if (!self) {
-            if (int rc = ws(WS_QC, (size_t)n_qry * 2, &d_qc)) return rc;
-            PPB_CUDA(cudaMemcpyAsync(d_qc, qry_cluster, (size_t)n_qry * 2, cudaMemcpyHostToDevice, s_compute.s));
-        }
-    }
-    if (int rc = ws(WS_DEG, 8, &d_deg)) return rc;
-    PPB_CUDA(cudaMemsetAsync(d_deg, 0, 8, s_compute.s));
-
-    // Row chunks: kernel(c) on s_compute overlaps D2H(c-1, c-2, ...) on s_copy.  Chunks end on row-TILE
-    // boundaries (kTI genomes of the row side), so no tile is computed by two launches, and they rotate through
-    // a ring of up to kHostRing device buffers: the result leaves over PCIe at about the rate the kernel
-    // produces it (8 B/pair), so the ring — not a double buffer — is what absorbs the jitter between the two.
-    const int rb = out_row_bytes(out_mode, K);
-    const int64_t per_row = (out ? rb : 0) + (labels ? 1 : 0);
-    size_t free_b = 0, total_b = 0;
-    PPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    // Results bound for pageable memory (a plain NumPy array) are staged: D2H into a pinned ring, then a consumer
-    // thread memcpy's each chunk out with a few threads while the GPU works on the next ones.  A direct
-    // cudaMemcpyAsync into pageable memory would be staged by the driver, serially, at a fraction of the link rate.
-    const bool staged = (out && !is_dma_able(out)) || (labels && !is_dma_able(labels));
-    int64_t cap = staged ? (int64_t)1 << 24   // 128 MiB of float2 per pinned staging buffer
-                         : (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per buffer
-    if (const char *e = std::getenv("PPB_HOST_CHUNK_ROWS")) cap = std::max<int64_t>(1024, atoll(e));
-    while (cap > 1024 && (size_t)(2 * cap * per_row) > free_b / 2) cap >>= 1;
-    std::vector<std::pair<int64_t, int64_t>> chunks;
-    plan_chunks(n_ref, n_qry, self, row_begin, row_end, cap, &chunks);
-    int64_t max_chunk = 0;
-    for (auto &c : chunks) max_chunk = std::max(max_chunk, c.second - c.first);
-    int n_buf = (int)std::min<size_t>(chunks.size(), kHostRing);
-    while (n_buf > 2 && (size_t)n_buf * max_chunk * per_row > free_b / 2) n_buf--;
-    if (const char *e = std::getenv("PPB_HOST_RING")) n_buf = std::max(1, std::min(atoi(e), (int)kHostRing));
-    n_buf = std::max(1, std::min<int>(n_buf, (int)chunks.size()));
-    const bool trace = std::getenv("PPB_HOST_TRACE") != nullptr;
-
-    void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {}, *h_out[kHostRing] = {}, *h_lab[kHostRing] = {};
-    Event done_compute[kHostRing], done_copy[kHostRing];
-    for (int b = 0; b < n_buf; b++) {
-        if (out)
-            if (int rc = ws(WS_OUT0 + b, (size_t)max_chunk * rb, &d_out[b])) return rc;
-        if (labels)
-            if (int rc = ws(WS_LAB0 + b, (size_t)max_chunk, &d_lab[b])) return rc;
-        if (staged && out)
-            if (int rc = g_ws.get_pinned(device_id, b, (size_t)max_chunk * rb, &h_out[b])) return rc;
-        if (staged && labels)
-            if (int rc = g_ws.get_pinned(device_id, (int)kHostRing + b, (size_t)max_chunk, &h_lab[b])) return rc;
-        PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
-        PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
-    }
-    std::vector<cudaEvent_t> tr;  // PPB_HOST_TRACE: (kernel begin, kernel end, copy begin, copy end) per chunk
-    cudaEvent_t tr_start = nullptr;
-    if (trace) {
-        tr.resize(chunks.size() * 4);
-        for (auto &e : tr) PPB_CUDA(cudaEventCreate(&e));
-        PPB_CUDA(cudaEventCreate(&tr_start));
-        PPB_CUDA(cudaEventRecord(tr_start, s_compute.s));
-    }
-    // one y-table for all launches of this call (same k-mers, table and sketch size throughout)
-    YtabLease lease;
-    if (out_mode == PPB_OUT_DISTS) {
-        const size_t entries = (size_t)(rand_table ? (size_t)n_clusters * n_clusters : 1) * K * ((size_t)64 * sketchsize64 + 1);
-        if (entries * sizeof(double) <= ((size_t)64 << 20)) {
-            void *q = nullptr;
-            if (int rc = ws(WS_YTAB, entries * sizeof(double), &q)) return rc;
-            lease.buf = (double *)q;
-            lease.capacity = entries;
-        }
-    }
-    struct LeaseScope {  // the lease is visible to the launches of THIS call only, whatever path leaves it
-        explicit LeaseScope(YtabLease *l) { g_ytab_lease = l; }
-        ~LeaseScope() { g_ytab_lease = nullptr; }
-    } lease_scope(lease.buf ? &lease : nullptr);
-    // staged mode: per-chunk "landed in the pinned ring" events, and the consumer thread that empties the ring
-    std::vector<cudaEvent_t> landed(staged ? chunks.size() : 0, nullptr);
-    for (auto &e : landed) PPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    std::mutex mu;
-    std::condition_variable cv;
-    size_t n_enqueued = 0, n_consumed = 0;  // chunks whose D2H is enqueued / whose staging slot is free again
-    bool abort_consumer = false, consumer_failed = false;
-    const int copy_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
-    std::thread consumer;
-    if (staged)
-        consumer = std::thread([&] {
-            cudaSetDevice(device_id);
-            for (size_t c = 0; c < chunks.size(); c++) {
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return n_enqueued > c || abort_consumer; });
-                    if (abort_consumer) return;
-                }
-                if (cudaEventSynchronize(landed[c]) != cudaSuccess) consumer_failed = true;
-                const int b = (int)(c % n_buf);
-                const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
-                if (out && !consumer_failed)
-                    parallel_memcpy((char *)out + (size_t)(r0 - row_begin) * rb, h_out[b], (size_t)(r1 - r0) * rb, copy_threads);
-                if (labels && !consumer_failed) parallel_memcpy(labels + (r0 - row_begin), h_lab[b], (size_t)(r1 - r0), copy_threads);
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    n_consumed = c + 1;
-                }
-                cv.notify_all();
-            }
-        });
-    struct ConsumerJoin {  // every exit path below stops and joins the consumer
-        std::thread &t;
-        std::mutex &mu;
-        std::condition_variable &cv;
-        bool &abort_flag;
-        bool finished = false;
-        ~ConsumerJoin() {
-            if (!t.joinable()) return;
-            if (!finished) {
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    abort_flag = true;
-                }
-                cv.notify_all();
-            }
-            t.join();
-        }
-    } joiner{consumer, mu, cv, abort_consumer};
-    for (size_t c = 0; c < chunks.size(); c++) {
-        const int b = (int)(c % n_buf);
-        const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
-        if (c >= (size_t)n_buf) PPB_CUDA(cudaStreamWaitEvent(s_compute.s, done_copy[b].e, 0));  // buffer b drained
-        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c], s_compute.s));
-        if (int rc = ppb_query_dev((const uint32_t *)d_ref, n_ref, self ? nullptr : (const uint32_t *)d_qry, n_qry,
-                                   kmers, K, sketchsize64, (const float *)d_tab, n_clusters,
-                                   (const uint16_t *)d_rc, (const uint16_t *)d_qc, r0, r1, out_mode,
-                                   out ? d_out[b] : nullptr, boundary, labels ? (int8_t *)d_lab[b] : nullptr,
-                                   (unsigned long long *)d_deg, s_compute.s))
-            return rc;
-        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 1], s_compute.s));
-        PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
-        PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
-        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 2], s_copy.s));
-        if (staged && c >= (size_t)n_buf) {  // staging slot b must have been emptied by the consumer
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return n_consumed + n_buf > c; });
-        }
-        if (out)
-            PPB_CUDA(cudaMemcpyAsync(staged ? h_out[b] : (void *)((char *)out + (size_t)(r0 - row_begin) * rb), d_out[b],
-                                     (size_t)(r1 - r0) * rb, cudaMemcpyDeviceToHost, s_copy.s));
-        if (labels)
-            PPB_CUDA(cudaMemcpyAsync(staged ? h_lab[b] : (void *)(labels + (r0 - row_begin)), d_lab[b], (size_t)(r1 - r0),
-                                     cudaMemcpyDeviceToHost, s_copy.s));
-        if (trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 3], s_copy.s));
-        PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
-        if (staged) {
-            PPB_CUDA(cudaEventRecord(landed[c], s_copy.s));
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                n_enqueued = c + 1;
-            }
-            cv.notify_all();
-        }
-    }
-    unsigned long long deg = 0;
-    PPB_CUDA(cudaMemcpyAsync(&deg, d_deg, 8, cudaMemcpyDeviceToHost, s_compute.s));
-    PPB_CUDA(cudaStreamSynchronize(s_compute.s));
-    PPB_CUDA(cudaStreamSynchronize(s_copy.s));
-    if (staged) {
-        joiner.finished = true;
-        consumer.join();
-        for (auto &e : landed) cudaEventDestroy(e);
-        if (consumer_failed) return fail(PPB_ERR_CUDA, "ppb_query_host: a device-to-host copy failed");
-    }
-    if (trace) {  // one line per chunk on stderr: when its kernel and its copy ran, relative to the first launch
-        double k_sum = 0, c_sum = 0;
-        for (size_t c = 0; c < chunks.size(); c++) {
-            float t[4];
-            for (int e = 0; e < 4; e++) cudaEventElapsedTime(&t[e], tr_start, tr[4 * c + e]);
-            k_sum += t[1] - t[0];
-            c_sum += t[3] - t[2];
-            std::fprintf(stderr, "[ppb_query_host] chunk %3zu rows %lld  kernel %8.2f..%8.2f ms  copy %8.2f..%8.2f ms\n", c,
-                         (long long)(chunks[c].second - chunks[c].first), t[0], t[1], t[2], t[3]);
-        }
-        std::fprintf(stderr, "[ppb_query_host] %zu chunks, ring of %d: kernels %.1f ms, copies %.1f ms\n", chunks.size(),
-                     n_buf, k_sum, c_sum);
-        for (auto &e : tr) cudaEventDestroy(e);
-        cudaEventDestroy(tr_start);
-    }
-    if (n_degenerate) *n_degenerate = (int64_t)deg;
-    return PPB_OK;
-}
+}  // extern "C++"
 
 int64_t ppb_plan_tiles(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_begin, int64_t row_end, int32_t tile_cols,
                        int32_t band_tiles, int32_t *tiles, int64_t max_tiles) {
@@ -1227,34 +920,6 @@ int64_t ppb_plan_host_chunks(int64_t n_ref, int64_t n_qry, int32_t self, int64_t
     return (int64_t)chunks.size();
 }
 
-int ppb_release_workspace(void) {
-    std::lock_guard<std::mutex> lk(g_ws.mu);
-    g_ws.release();
-    int dev = 0;
-    cudaMemPool_t pool;  // the stream-ordered scratch cached by the iteration / kNN entry points
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        cudaDeviceSynchronize();
-        cudaMemPoolTrimTo(pool, 0);
-    }
-    cudaGetLastError();
-    return PPB_OK;
-}
-
-int ppb_assign_threshold_host(const float *dists, int64_t n, int32_t slope, float x_max, float y_max, float *out,
-                              int32_t device_id) {
-    if (n < 0 || (n > 0 && (!dists || !out))) return fail(PPB_ERR_ARG, "ppb_assign_threshold_host: bad argument");
-    if (n == 0) return PPB_OK;
-    int ndev = ppb_device_count();
-    if (ndev <= 0) return fail(PPB_ERR_NO_DEVICE, "ppb_assign_threshold_host: no CUDA device (no CPU path)");
-    if (device_id < 0 || device_id >= ndev) return fail(PPB_ERR_ARG, "ppb_assign_threshold_host: bad device id");
-    PPB_CUDA(cudaSetDevice(device_id));
-    DevBuf d_in, d_o;
-    if (int rc = d_in.alloc((size_t)n * 8)) return rc;
-    if (int rc = d_o.alloc((size_t)n * 4)) return rc;
-    PPB_CUDA(cudaMemcpy(d_in.p, dists, (size_t)n * 8, cudaMemcpyHostToDevice));
-    if (int rc = ppb_assign_threshold_dev((const float *)d_in.p, n, slope, x_max, y_max, (float *)d_o.p, nullptr)) return rc;
-    PPB_CUDA(cudaMemcpy(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    return PPB_OK;
-}
-
 }  // extern "C"
+
+#include "ppb_host.inl"

@@ -138,24 +138,34 @@ struct QueryParams {
 // ------------------------------------------------------------------------------------------------
 constexpr int kPackWarps = 8;
 
+// Where a packed part goes: this device's buffer and, in a single-process multi-GPU call, every peer's (NVLink-mapped)
+// buffer — each device packs 1/G of the genomes and stores them everywhere, so nobody uploads or packs the whole array.
+struct PackDsts {
+    uint32_t *p[PPB_MAX_PEERS];
+    int32_t n;
+};
+
+// Genomes [g_begin, g_end) of the full packed layout (n real genomes padded to n_pad; g >= n are zero sketches);
+// `src` holds only this part (genome g is src row idx[g - g_begin], or g - g_begin without an index list).
 __global__ void __launch_bounds__(kPackWarps * 32) pack_kernel(const uint64_t *__restrict__ src,
-                                                               const int64_t *__restrict__ idx, int64_t n, int64_t n_pad,
-                                                               int32_t K, int32_t ss64, int32_t n_slices,
-                                                               uint32_t *__restrict__ dst) {
+                                                               const int64_t *__restrict__ idx, int64_t g_begin,
+                                                               int64_t g_end, int64_t n, int64_t n_pad, int32_t K,
+                                                               int32_t ss64, int32_t n_slices, const PackDsts dsts) {
     __shared__ uint32_t stage[kPackWarps][kSliceWords];  // [column-in-slice (16)][plane (14)][half (2)] as uint32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t units = (int64_t)K * n_slices * n_pad;
+    const int64_t span = g_end - g_begin;
+    const int64_t units = (int64_t)K * n_slices * span;
     const int64_t W = (int64_t)ss64 * kBbits;
     uint32_t *sm = stage[warp];
     for (int64_t u = (int64_t)blockIdx.x * kPackWarps + warp; u < units; u += (int64_t)gridDim.x * kPackWarps) {
-        const int64_t g = u % n_pad;
-        const int32_t ks = (int32_t)(u / n_pad);
+        const int64_t gl = u % span, g = g_begin + gl;
+        const int32_t ks = (int32_t)(u / span);
         const int32_t k = ks / n_slices, sl = ks - k * n_slices;
         // uint64 columns 16*sl .. 16*sl+15 of this (genome, k): 224 consecutive words (fewer in the last slice)
         const int32_t col0 = sl * 16, n_cols = max(0, min(16, ss64 - col0));
         const int32_t n_words = g < n ? n_cols * kBbits : 0;
         const uint64_t *base = nullptr;
-        if (g < n) base = src + ((idx ? idx[g] : g) * K + k) * W + (int64_t)col0 * kBbits;
+        if (g < n) base = src + ((idx ? idx[gl] : gl) * K + k) * W + (int64_t)col0 * kBbits;
         __syncwarp();
         for (int w = lane; w < kSliceWords / 2; w += 32) {
             const uint64_t v = w < n_words ? __ldg(base + w) : 0ull;
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) pack_kernel(const uint64_t *_
             sm[2 * w + 1] = (uint32_t)(v >> 32);
         }
         __syncwarp();
-        uint32_t *out = dst + u * kSliceWords;
+        const int64_t out_off = ((int64_t)ks * n_pad + g) * kSliceWords;
         for (int o = lane; o < kSliceWords; o += 32) {
             int32_t l, plane;  // output word o = plane `plane` of group (lane) `l`, see the layout comment above
             if (o < 384) {
@@ -174,7 +184,8 @@ __global__ void __launch_bounds__(kPackWarps * 32) pack_kernel(const uint64_t *_
                 plane = 12 + (o & 1);
             }
             // group l = half (l & 1) of column (l >> 1); staged word index = (column * 14 + plane) * 2 + half
-            out[o] = sm[(((l >> 1) * kBbits + plane) << 1) + (l & 1)];
+            const uint32_t v = sm[(((l >> 1) * kBbits + plane) << 1) + (l & 1)];
+            for (int d = 0; d < dsts.n; d++) dsts.p[d][out_off + o] = v;
         }
     }
 }

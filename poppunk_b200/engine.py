@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import OUT_COUNTS, OUT_DISTS, OUT_JACCARD, BBITS, Boundary, check
 
 __all__ = ["PackedSketches", "pack", "query", "query_host", "assign_threshold", "num_rows", "shard_rows",
-           "query_sharded", "query_edges", "FusedExchange", "OUT_DISTS", "OUT_JACCARD", "OUT_COUNTS"]
+           "query_sharded", "query_edges", "FusedExchange", "host_result", "visible_devices", "OUT_DISTS", "OUT_JACCARD", "OUT_COUNTS"]
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -189,10 +189,54 @@ def assign_threshold(dists: torch.Tensor, slope: int, x_max: float, y_max: float
 # --------------------------------------------------------------------------------------------
 # host-buffer path (H2D + pack + kernels + D2H inside the library) — what the drop-in wrapper uses
 # --------------------------------------------------------------------------------------------
+def host_result(shape, dtype) -> np.ndarray:
+    """A NumPy array for a result the caller will own, backed by the library's host pool (``ppb_host_alloc``):
+    huge-page backed, and page-locked from the first time a block is reused, so that repeated calls of a process
+    receive their result by direct DMA.  The block returns to the pool when the array (and every view of it) dies."""
+    import weakref
+    L = _lib.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype=dtype)
+    ptr = L.ppb_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError(f"ppb_host_alloc({nbytes}) failed: {L.ppb_last_error().decode()}")
+    buf = (C.c_byte * nbytes).from_address(ptr)
+    weakref.finalize(buf, L.ppb_host_free, ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def visible_devices(first: int = 0):
+    """Devices a host-buffer call uses: every visible CUDA device, ``first`` (PopPUNK's ``deviceid``) leading.
+    ``PPB_DEVICES`` overrides: ``single`` = only ``first``; ``0,2,3`` = that list; an integer N = the first N."""
+    import os
+    L = _lib.load()
+    n = L.ppb_device_count()
+    if n <= 0:
+        raise RuntimeError("poppunk_b200: no CUDA device visible — this engine has no CPU fallback")
+    if not 0 <= first < n:
+        raise RuntimeError(f"poppunk_b200: device id {first} is not one of the {n} visible CUDA devices")
+    knob = os.environ.get("PPB_DEVICES", "").strip().lower()
+    if knob == "single":
+        return [first]
+    if "," in knob:
+        devs = [int(v) for v in knob.split(",") if v.strip() != ""]
+        if any(not 0 <= d < n for d in devs) or len(set(devs)) != len(devs):
+            raise RuntimeError(f"PPB_DEVICES={knob!r} does not name distinct visible devices (0..{n - 1})")
+        return devs
+    order = [first] + [d for d in range(n) if d != first]
+    if knob.isdigit() and int(knob) >= 1:
+        order = order[:int(knob)]
+    return order
+
+
 def query_host(ref: np.ndarray, qry: Optional[np.ndarray], kmers, rand_table=None, ref_cluster=None,
                qry_cluster=None, row_begin: int = 0, row_end: Optional[int] = None, out_mode: int = OUT_DISTS,
-               boundary=None, out: Optional[np.ndarray] = None, want_out: bool = True, device_id: int = 0):
-    """``ppb_query_host``: NumPy in, NumPy out.  Returns ``(out, labels, n_degenerate)``."""
+               boundary=None, out: Optional[np.ndarray] = None, want_out: bool = True, device_id: int = 0,
+               devices: Optional[Sequence[int]] = None):
+    """``ppb_query_host_multi``: NumPy in, NumPy out, on ``devices`` (default: the one ``device_id``).
+    Returns ``(out, labels, n_degenerate)``.  Without ``out`` the result array comes from :func:`host_result`."""
     L = _lib.load()
     if L.ppb_device_count() <= 0:
         raise RuntimeError("poppunk_b200: no CUDA device visible — this engine has no CPU fallback")
@@ -216,28 +260,34 @@ def query_host(ref: np.ndarray, qry: Optional[np.ndarray], kmers, rand_table=Non
     if rand_table is not None:
         rand_table = np.ascontiguousarray(rand_table, dtype=np.float32)
         C_ = rand_table.shape[0]
+        if rand_table.shape != (C_, C_, K):
+            raise ValueError("random-match table must be [C][C][K]")
         ref_cluster = np.ascontiguousarray(ref_cluster, dtype=np.uint16)
+        if ref_cluster.shape != (n_ref,) or (n_ref and int(ref_cluster.max()) >= C_):
+            raise ValueError("reference cluster ids must be one per genome and < C")
         if qry is not None:
             qry_cluster = np.ascontiguousarray(qry_cluster, dtype=np.uint16)
+            if qry_cluster.shape != (n_qry,) or (n_qry and int(qry_cluster.max()) >= C_):
+                raise ValueError("query cluster ids must be one per genome and < C")
     if want_out and out is None:
-        if out_mode == OUT_DISTS:
-            out = np.empty((rows, 2), dtype=np.float32)
-        elif out_mode == OUT_JACCARD:
-            out = np.empty((rows, K), dtype=np.float32)
-        else:
-            out = np.empty((rows, K), dtype=np.uint32)
+        width, dt = (2, np.float32) if out_mode == OUT_DISTS else (K, np.float32 if out_mode == OUT_JACCARD else np.uint32)
+        out = host_result((rows, width), dt)
+    elif out is not None and (not out.flags.c_contiguous or not out.flags.writeable):
+        raise ValueError("out must be a writeable C-contiguous array")
     bnd = _boundary(boundary)
     labels = np.empty(rows, dtype=np.int8) if bnd is not None else None
     ndeg = C.c_int64(0)
+    devs = [int(device_id)] if devices is None else [int(d) for d in devices]
+    dev_arr = (C.c_int32 * len(devs))(*devs)
 
     def ptr(a):
         return None if a is None else a.ctypes.data
 
-    check(L.ppb_query_host(ptr(ref), n_ref, ptr(qry), n_qry, ptr(kmers_np), K, ss64, BBITS, ptr(rand_table), C_,
-                           ptr(ref_cluster) if rand_table is not None else None,
-                           ptr(qry_cluster) if (rand_table is not None and qry is not None) else None,
-                           row_begin, row_end, out_mode, ptr(out), C.byref(bnd) if bnd is not None else None,
-                           ptr(labels), C.byref(ndeg), device_id), "ppb_query_host")
+    check(L.ppb_query_host_multi(ptr(ref), n_ref, ptr(qry), n_qry, ptr(kmers_np), K, ss64, BBITS, ptr(rand_table), C_,
+                                 ptr(ref_cluster) if rand_table is not None else None,
+                                 ptr(qry_cluster) if (rand_table is not None and qry is not None) else None,
+                                 row_begin, row_end, out_mode, ptr(out), C.byref(bnd) if bnd is not None else None,
+                                 ptr(labels), C.byref(ndeg), dev_arr, len(devs)), "ppb_query_host_multi")
     return out, labels, int(ndeg.value)
 
 
