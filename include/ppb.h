@@ -295,6 +295,12 @@ int ppb_assign_threshold_host(const float *dists, int64_t n, int32_t slope,
  * LOP3+POPC mixed (mode 2) kernel on `stream` and returns lane-ops executed; caller times it. */
 int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *lane_ops, void *stream);
 
+/* The distance kernel's column body (LDS + 14 LOP3 per row and 32 bins + POPC + pack + REDUX + STS) as a stand-alone
+ * loop with rows_per_warp (4, 5 or 8) register-stationary rows and warps_per_scheduler (1..4) warps per SM scheduler,
+ * one CTA per SM, no barriers: how much of the LOP3 pipe that instruction mix can reach.  Returns LOP3 lane-ops.   */
+int ppb_microbench_mix_dev(int32_t rows_per_warp, int32_t warps_per_scheduler, int32_t with_lds, int64_t iters,
+                           uint32_t *d_sink, int64_t *lop3_lane_ops, void *stream);
+
 /* kernel launch counter since library load (for bench.py's gpu_launches). */
 int64_t ppb_launch_count(void);
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev", "ppb_plan_host_chunks",
     "ppb_generate_all_tuples_dev", "ppb_threshold_iterate_1d_dev", "ppb_threshold_iterate_2d_dev", "ppb_knn_dev",
     "ppb_lower_rank_dev", "ppb_extend_dev", "ppb_plan_tiles", "ppb_pack_part_dev", "ppb_query_host_multi",
-    "ppb_plan_device_shards", "ppb_host_alloc", "ppb_host_free", "ppb_host_pool_stats",
+    "ppb_plan_device_shards", "ppb_host_alloc", "ppb_host_free", "ppb_host_pool_stats", "ppb_microbench_mix_dev",
 ]
 
 
@@ -124,6 +124,8 @@ def load():
     L.ppb_plan_host_chunks.restype = i64
     L.ppb_microbench_dev.argtypes = [i32, i64, vp, vp, vp]
     L.ppb_microbench_dev.restype = C.c_int
+    L.ppb_microbench_mix_dev.argtypes = [i32, i32, i32, i64, vp, vp, vp]
+    L.ppb_microbench_mix_dev.restype = C.c_int
     _lib = L
     return L
 

@@ -254,6 +254,11 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (sketchsize64 < 1 || sketchsize64 > 1023)
         return fail(PPB_ERR_ARG, "ppb_query_dev: sketchsize64 must be in [1, 1023] (uint16 per-k counts)");
     if (out_mode < PPB_OUT_DISTS || out_mode > PPB_OUT_COUNTS) return fail(PPB_ERR_ARG, "ppb_query_dev: bad out_mode");
+    {   // an empty row range is a no-op whatever the buffers are (torch hands out null pointers for empty tensors, and
+        // a rank with an empty shard must still reach the collectives that follow)
+        const int64_t all_rows = ppb_num_rows(n_ref, n_qry, self);
+        if (row_begin >= 0 && row_begin == row_end && row_end <= all_rows) return PPB_OK;
+    }
     const bool has_peers = (n_peers > 0 && d_peer_out) || d_mc_out;
     if (n_peers < 0 || n_peers > PPB_MAX_PEERS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: bad n_peers");
     if (has_peers && out_mode != PPB_OUT_DISTS) return fail(PPB_ERR_ARG, "ppb_query_dev_fused: PPB_OUT_DISTS only");
@@ -399,7 +404,7 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
                 lease->filled = true;
             }
             p.ytab = lease->buf;
-        } else if (entries * sizeof(double) <= ((size_t)64 << 20)) {
+        } else if (entries * sizeof(double) <= ((size_t)64 << 20) && !std::getenv("PPB_NO_YTAB")) {
             PPB_CUDA(cudaMallocAsync(&d_ytab, entries * sizeof(double), st));
             const int threads = 256;
             const unsigned blocks = (unsigned)std::min<size_t>((entries + threads - 1) / threads, (size_t)sms * 8);
@@ -863,6 +868,29 @@ int ppb_microbench_dev(int32_t mode, int64_t iters, uint32_t *d_sink, int64_t *l
     PPB_CUDA(cudaGetLastError());
     // lane-ops of the op being measured (mode 2 counts its LOP3s)
     if (lane_ops) *lane_ops = (int64_t)grid * threads * iters * per_thread_iter;
+    return PPB_OK;
+}
+
+int ppb_microbench_mix_dev(int32_t rows_per_warp, int32_t warps_per_scheduler, int32_t with_lds, int64_t iters,
+                           uint32_t *d_sink, int64_t *lop3_lane_ops, void *stream) {
+    const int max_w = rows_per_warp == 8 ? 2 : rows_per_warp == 5 ? 3 : rows_per_warp == 4 ? 4 : 0;  // what the register file holds
+    if (warps_per_scheduler < 1 || warps_per_scheduler > max_w || iters < 1 || !d_sink)
+        return fail(PPB_ERR_ARG, "ppb_microbench_mix_dev: (rows_per_warp, warps_per_scheduler) must be (8, <=2), (5, <=3) or (4, <=4)");
+    int dev = 0, sms = 0;
+    PPB_CUDA(cudaGetDevice(&dev));
+    if (int rc = num_sms(dev, &sms)) return rc;
+    const unsigned threads = 128u * warps_per_scheduler;
+    const size_t smem = 4 * ppb::kSliceBytes + 16 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows_per_warp == 8)
+        ppb::mixbench_kernel<8, 256><<<sms, threads, smem, st>>>(iters, d_sink, 12345u, with_lds);
+    else if (rows_per_warp == 5)
+        ppb::mixbench_kernel<5, 384><<<sms, threads, smem, st>>>(iters, d_sink, 12345u, with_lds);
+    else
+        ppb::mixbench_kernel<4, 512><<<sms, threads, smem, st>>>(iters, d_sink, 12345u, with_lds);
+    g_launches++;
+    PPB_CUDA(cudaGetLastError());
+    if (lop3_lane_ops) *lop3_lane_ops = (int64_t)sms * threads * iters * 4 * rows_per_warp * 14;
     return PPB_OK;
 }
 

@@ -80,7 +80,7 @@ constexpr int kHostRing = 8;  // result buffers per device (chunks in flight bet
 constexpr int kUpRing = 4;    // pinned staging buffers of a pageable upload
 constexpr size_t kUpPiece = (size_t)16 << 20;
 enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
-enum { PIN_OUT0 = 0, PIN_LAB0 = kHostRing, PIN_UP0 = 2 * kHostRing };
+enum { PIN_OUT0 = 0, PIN_UP0 = 16 };
 
 // true when the CUDA driver can DMA straight into / out of p (pinned / registered / managed host memory)
 bool is_dma_able(const void *p) {
@@ -330,8 +330,7 @@ int host_worker(HostJob &job, int g) {
         const int64_t per_row = (job.out ? rb : 0) + (job.labels ? 1 : 0);
         size_t free_b = 0, total_b = 0;
         PPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        int64_t cap = job.staged ? (int64_t)1 << 24   // 128 MiB of float2 per pinned staging buffer
-                                 : (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per buffer
+        int64_t cap = (int64_t)1 << 26;  // 64 Mi rows = 512 MiB of float2 per device buffer
         if (const char *e = std::getenv("PPB_HOST_CHUNK_ROWS")) cap = std::max<int64_t>(1024, atoll(e));
         while (cap > 1024 && (size_t)(2 * cap * per_row) > free_b / 2) cap >>= 1;
         // rows of this device, in the coordinates of the launch (non-self: relative to its own query range)
@@ -340,24 +339,20 @@ int host_worker(HostJob &job, int g) {
         plan_chunks(job.n_ref, n_q, job.self, r_lo - shift, r_hi - shift, cap, &chunks);
         int64_t max_chunk = 0;
         for (auto &c : chunks) max_chunk = std::max(max_chunk, c.second - c.first);
-        int n_buf = (int)std::min<size_t>(chunks.size(), kHostRing);
+        int n_buf = (int)std::min<size_t>(chunks.size(), job.staged ? 4 : kHostRing);
         while (n_buf > 2 && (size_t)n_buf * max_chunk * per_row > free_b / 2) n_buf--;
         if (const char *e = std::getenv("PPB_HOST_RING")) n_buf = std::max(1, std::min(atoi(e), kHostRing));
         n_buf = std::max(1, std::min<int>(n_buf, (int)chunks.size()));
 
         char *out_base = job.out ? (char *)job.out - (size_t)(job.row_begin - shift) * rb : nullptr;  // row r of the launch -> out_base + r*rb
         int8_t *lab_base = job.labels ? job.labels - (job.row_begin - shift) : nullptr;
-        void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {}, *h_out[kHostRing] = {}, *h_lab[kHostRing] = {};
+        void *d_out[kHostRing] = {}, *d_lab[kHostRing] = {};
         Event done_compute[kHostRing], done_copy[kHostRing];
         for (int b = 0; b < n_buf; b++) {
             if (job.out)
                 if (int rc = ws.get(WS_OUT0 + b, (size_t)max_chunk * rb, &d_out[b])) return rc;
             if (job.labels)
                 if (int rc = ws.get(WS_LAB0 + b, (size_t)max_chunk, &d_lab[b])) return rc;
-            if (job.staged && job.out)
-                if (int rc = ws.get_pinned(PIN_OUT0 + b, (size_t)max_chunk * rb, &h_out[b])) return rc;
-            if (job.staged && job.labels)
-                if (int rc = ws.get_pinned(PIN_LAB0 + b, (size_t)max_chunk, &h_lab[b])) return rc;
             PPB_CUDA(cudaEventCreateWithFlags(&done_compute[b].e, cudaEventDisableTiming));
             PPB_CUDA(cudaEventCreateWithFlags(&done_copy[b].e, cudaEventDisableTiming));
         }
@@ -384,8 +379,47 @@ int host_worker(HostJob &job, int g) {
             explicit LeaseScope(YtabLease *l) { g_ytab_lease = l; }
             ~LeaseScope() { g_ytab_lease = nullptr; }
         } lease_scope(lease.buf ? &lease : nullptr);
-        // staged mode: per-chunk "landed in the pinned ring" events, and the consumer thread that empties the ring
-        std::vector<cudaEvent_t> landed(job.staged ? chunks.size() : 0, nullptr);
+
+        // ---- staged mode (pageable destination).  A finished chunk leaves the device in TRANSFERS of <= kXferBytes:
+        // D2H into a ring of pinned slots, and a pool of copy threads drains the slots into the caller's pages in
+        // 4 MiB pieces (claimed from one shared counter, so no thread idles at a chunk boundary).  First touch of the
+        // destination (2 MiB faults after MADV_HUGEPAGE) happens inside those memcpys: the host cores, not PCIe, set
+        // the pace of a first call (tools/host_floor.cu: ~40 GB/s with all cores of the 16-vCPU B200 host).
+        struct Xfer {
+            size_t chunk;
+            const char *d_src;   // device address
+            char *dst;           // final host address
+            size_t len;
+            size_t piece0;       // index of its first piece
+        };
+        constexpr size_t kXferBytes = (size_t)32 << 20, kPieceBytes = (size_t)4 << 20;
+        constexpr int kPinRing = 8;
+        std::vector<Xfer> xfers;
+        std::vector<size_t> chunk_x0(chunks.size() + 1, 0);  // transfers of chunk c: [chunk_x0[c], chunk_x0[c+1])
+        size_t n_pieces = 0;
+        void *pin[kPinRing] = {};
+        int n_pin = 0;
+        if (job.staged) {
+            for (size_t c = 0; c < chunks.size(); c++) {
+                const int b = (int)(c % n_buf);
+                const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
+                chunk_x0[c] = xfers.size();
+                auto add = [&](const char *d_base, char *h_base, size_t bytes) {
+                    for (size_t off = 0; off < bytes; off += kXferBytes) {
+                        const size_t len = std::min(kXferBytes, bytes - off);
+                        xfers.push_back(Xfer{c, d_base + off, h_base + off, len, n_pieces});
+                        n_pieces += (len + kPieceBytes - 1) / kPieceBytes;
+                    }
+                };
+                if (job.out) add((const char *)d_out[b], out_base + (size_t)r0 * rb, (size_t)(r1 - r0) * rb);
+                if (job.labels) add((const char *)d_lab[b], (char *)(lab_base + r0), (size_t)(r1 - r0));
+            }
+            chunk_x0[chunks.size()] = xfers.size();
+            n_pin = (int)std::min<size_t>(kPinRing, xfers.size());
+            for (int q = 0; q < n_pin; q++)
+                if (int rc = ws.get_pinned(PIN_OUT0 + q, kXferBytes, &pin[q])) return rc;
+        }
+        std::vector<cudaEvent_t> landed(xfers.size(), nullptr);  // transfer t has arrived in its pinned slot
         for (auto &e : landed) PPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         struct LandedScope {
             std::vector<cudaEvent_t> &v;
@@ -396,40 +430,47 @@ int host_worker(HostJob &job, int g) {
         } landed_scope{landed};
         std::mutex mu;
         std::condition_variable cv;
-        size_t n_enqueued = 0, n_consumed = 0;  // chunks whose D2H is enqueued / whose staging slot is free again
-        bool abort_consumer = false, consumer_failed = false;
-        std::thread consumer;
-        if (job.staged)
-            consumer = std::thread([&] {
-                cudaSetDevice(dev);
-                for (size_t c = 0; c < chunks.size(); c++) {
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [&] { return n_enqueued > c || abort_consumer; });
-                        if (abort_consumer) return;
-                    }
-                    if (cudaEventSynchronize(landed[c]) != cudaSuccess) consumer_failed = true;
-                    const int b = (int)(c % n_buf);
-                    const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
-                    if (job.out && !consumer_failed)
-                        parallel_memcpy(out_base + (size_t)r0 * rb, h_out[b], (size_t)(r1 - r0) * rb, job.copy_threads);
-                    if (job.labels && !consumer_failed)
-                        parallel_memcpy(lab_base + r0, h_lab[b], (size_t)(r1 - r0), job.copy_threads);
-                    {
-                        std::lock_guard<std::mutex> lk(mu);
-                        n_consumed = c + 1;
-                    }
-                    cv.notify_all();
+        size_t n_enqueued = 0, n_drained = 0;          // transfers whose D2H is enqueued / whose slot is free again (in order)
+        std::vector<int> pieces_left(xfers.size(), 0);   // per transfer, under mu
+        std::vector<char> drained(xfers.size(), 0);
+        for (size_t t = 0; t < xfers.size(); t++) pieces_left[t] = (int)((xfers[t].len + kPieceBytes - 1) / kPieceBytes);
+        std::atomic<size_t> next_piece{0};
+        bool abort_copy = false;
+        std::atomic<bool> copy_failed{false};
+        auto copy_worker = [&] {
+            cudaSetDevice(dev);
+            size_t t = 0;
+            for (;;) {
+                const size_t p = next_piece.fetch_add(1);
+                if (p >= n_pieces) return;
+                while (t + 1 < xfers.size() && xfers[t + 1].piece0 <= p) t++;   // pieces are claimed in increasing order
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return n_enqueued > t || abort_copy; });
+                    if (abort_copy) return;
                 }
-            });
-        struct ConsumerJoin {  // every exit path below stops and joins the consumer
-            std::thread &t;
+                if (cudaEventSynchronize(landed[t]) != cudaSuccess) copy_failed = true;
+                const Xfer &x = xfers[t];
+                const size_t off = (p - x.piece0) * kPieceBytes, len = std::min(kPieceBytes, x.len - off);
+                if (!copy_failed) std::memcpy(x.dst + off, (const char *)pin[t % n_pin] + off, len);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (--pieces_left[t] == 0) {
+                        drained[t] = 1;
+                        while (n_drained < xfers.size() && drained[n_drained]) n_drained++;
+                        cv.notify_all();
+                    }
+                }
+            }
+        };
+        std::vector<std::thread> copiers;
+        struct CopierJoin {  // every exit path below stops and joins the copy threads
+            std::vector<std::thread> &v;
             std::mutex &mu;
             std::condition_variable &cv;
             bool &abort_flag;
             bool finished = false;
-            ~ConsumerJoin() {
-                if (!t.joinable()) return;
+            ~CopierJoin() {
                 if (!finished) {
                     {
                         std::lock_guard<std::mutex> lk(mu);
@@ -437,9 +478,34 @@ int host_worker(HostJob &job, int g) {
                     }
                     cv.notify_all();
                 }
-                t.join();
+                for (auto &t : v)
+                    if (t.joinable()) t.join();
             }
-        } joiner{consumer, mu, cv, abort_consumer};
+        } joiner{copiers, mu, cv, abort_copy};
+        if (job.staged)
+            for (int t = 0; t < job.copy_threads; t++) copiers.emplace_back(copy_worker);
+        // transfers of chunk c: enqueued AFTER the launch of chunk c+1, so the host thread's waits for free pinned slots
+        // never hold back a kernel
+        auto enqueue_transfers = [&](size_t c) -> int {
+            const int b = (int)(c % n_buf);
+            if (job.trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 2], s_copy.s));
+            for (size_t t = chunk_x0[c]; t < chunk_x0[c + 1]; t++) {
+                if (t >= (size_t)n_pin) {  // slot t % n_pin must have been emptied by the copy threads
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return n_drained + n_pin > t; });
+                }
+                PPB_CUDA(cudaMemcpyAsync(pin[t % n_pin], xfers[t].d_src, xfers[t].len, cudaMemcpyDeviceToHost, s_copy.s));
+                PPB_CUDA(cudaEventRecord(landed[t], s_copy.s));
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    n_enqueued = t + 1;
+                }
+                cv.notify_all();
+            }
+            if (job.trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 3], s_copy.s));
+            PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
+            return PPB_OK;
+        };
         for (size_t c = 0; c < chunks.size(); c++) {
             const int b = (int)(c % n_buf);
             const int64_t r0 = chunks[c].first, r1 = chunks[c].second;
@@ -453,29 +519,27 @@ int host_worker(HostJob &job, int g) {
                 return rc;
             if (job.trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 1], s_compute.s));
             PPB_CUDA(cudaEventRecord(done_compute[b].e, s_compute.s));
+            if (job.staged) {
+                // (with a single device buffer the next launch needs this chunk's copies first)
+                if (c > 0 && n_buf > 1)
+                    if (int rc = enqueue_transfers(c - 1)) return rc;
+                PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
+                if (n_buf == 1)
+                    if (int rc = enqueue_transfers(c)) return rc;
+                continue;
+            }
             PPB_CUDA(cudaStreamWaitEvent(s_copy.s, done_compute[b].e, 0));
             if (job.trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 2], s_copy.s));
-            if (job.staged && c >= (size_t)n_buf) {  // staging slot b must have been emptied by the consumer
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return n_consumed + n_buf > c; });
-            }
             if (job.out)
-                PPB_CUDA(cudaMemcpyAsync(job.staged ? h_out[b] : (void *)(out_base + (size_t)r0 * rb), d_out[b],
-                                         (size_t)(r1 - r0) * rb, cudaMemcpyDeviceToHost, s_copy.s));
+                PPB_CUDA(cudaMemcpyAsync(out_base + (size_t)r0 * rb, d_out[b], (size_t)(r1 - r0) * rb, cudaMemcpyDeviceToHost,
+                                         s_copy.s));
             if (job.labels)
-                PPB_CUDA(cudaMemcpyAsync(job.staged ? h_lab[b] : (void *)(lab_base + r0), d_lab[b], (size_t)(r1 - r0),
-                                         cudaMemcpyDeviceToHost, s_copy.s));
+                PPB_CUDA(cudaMemcpyAsync(lab_base + r0, d_lab[b], (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s_copy.s));
             if (job.trace) PPB_CUDA(cudaEventRecord(tr[4 * c + 3], s_copy.s));
             PPB_CUDA(cudaEventRecord(done_copy[b].e, s_copy.s));
-            if (job.staged) {
-                PPB_CUDA(cudaEventRecord(landed[c], s_copy.s));
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    n_enqueued = c + 1;
-                }
-                cv.notify_all();
-            }
         }
+        if (job.staged && n_buf > 1)
+            if (int rc = enqueue_transfers(chunks.size() - 1)) return rc;
         unsigned long long deg = 0;
         PPB_CUDA(cudaMemcpyAsync(&deg, d_deg, 8, cudaMemcpyDeviceToHost, s_compute.s));
         PPB_CUDA(cudaStreamSynchronize(s_compute.s));
@@ -483,21 +547,28 @@ int host_worker(HostJob &job, int g) {
         job.deg[g] = deg;
         if (job.staged) {
             joiner.finished = true;
-            consumer.join();
-            if (consumer_failed) return fail(PPB_ERR_CUDA, "ppb_query_host: a device-to-host copy failed");
+            for (auto &t : copiers) t.join();
+            if (copy_failed) return fail(PPB_ERR_CUDA, "ppb_query_host: a device-to-host copy failed");
         }
-        if (job.trace) {  // one line per chunk on stderr: when its kernel and its copy ran, relative to the first launch
+        if (job.trace) {  // when each chunk's kernel and copies ran, relative to the first launch
             double k_sum = 0, c_sum = 0;
+            float first_copy = 0, last_copy = 0;
             for (size_t c = 0; c < chunks.size(); c++) {
                 float t[4];
                 for (int e = 0; e < 4; e++) cudaEventElapsedTime(&t[e], tr_start, tr[4 * c + e]);
                 k_sum += t[1] - t[0];
                 c_sum += t[3] - t[2];
-                std::fprintf(stderr, "[ppb_query_host dev %d] chunk %3zu rows %lld  kernel %8.2f..%8.2f ms  copy %8.2f..%8.2f ms\n",
-                             dev, c, (long long)(chunks[c].second - chunks[c].first), t[0], t[1], t[2], t[3]);
+                if (c == 0) first_copy = t[2];
+                last_copy = t[3];
+                if (std::getenv("PPB_HOST_TRACE")[0] == '2')
+                    std::fprintf(stderr, "[ppb_query_host dev %d] chunk %3zu rows %lld  kernel %8.2f..%8.2f ms  copy %8.2f..%8.2f ms\n",
+                                 dev, c, (long long)(chunks[c].second - chunks[c].first), t[0], t[1], t[2], t[3]);
             }
-            std::fprintf(stderr, "[ppb_query_host dev %d] %zu chunks, ring of %d: kernels %.1f ms, copies %.1f ms\n", dev,
-                         chunks.size(), n_buf, k_sum, c_sum);
+            std::fprintf(stderr,
+                         "[ppb_query_host dev %d] rows %lld in %zu chunks (device ring %d%s): kernels %.1f ms, copies %.1f ms "
+                         "(first starts at %.1f, last ends at %.1f ms after the first launch)\n",
+                         dev, (long long)(r_hi - r_lo), chunks.size(), n_buf, job.staged ? ", staged" : ", direct DMA", k_sum, c_sum,
+                         first_copy, last_copy);
             for (auto &e : tr) cudaEventDestroy(e);
             cudaEventDestroy(tr_start);
         }
@@ -633,7 +704,8 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
         CPU_ZERO(&set);
         if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
     }
-    job.copy_threads = std::max(1, std::min(8, hw / (2 * G) + (G > 1 ? 1 : 0)));
+    // copy threads per device (staged results, pageable uploads): all cores but one per device worker and one spare
+    job.copy_threads = std::max(2, std::min(16, (hw - 1 - G) / G));
     if (const char *e = std::getenv("PPB_COPY_THREADS")) job.copy_threads = std::max(1, atoi(e));
     if (job.staged) {
         if (out) advise_hugepages(out, (size_t)(row_end - row_begin) * out_row_bytes(out_mode, K));

@@ -64,6 +64,22 @@ constexpr int kStages = PPB_STAGES;
 #ifndef PPB_DUAL_RING
 #define PPB_DUAL_RING 0
 #endif
+// Compute-warp pipeline options (measured in profiles/r02_experiments.md):
+//   PPB_STAGE_INC   ring stage index / barrier address / parity kept incrementally (no div/mod chain of uniform
+//                   instructions in front of every stage's try_wait)
+//   PPB_EARLY_PROBE the next stage's barrier is tested (non-blocking) before the stage's last column, so the wait at
+//                   the stage boundary is a predicate test when the data is already there
+//   PPB_DEFER_PACK  the IMAD that packs the second half's popcounts runs in the NEXT column, after its first LOP3 block
+#ifndef PPB_STAGE_INC
+#define PPB_STAGE_INC 0
+#endif
+#ifndef PPB_EARLY_PROBE
+#define PPB_EARLY_PROBE 0
+#endif
+#ifndef PPB_DEFER_PACK
+#define PPB_DEFER_PACK 0
+#endif
+static_assert(!(PPB_STAGE_INC && PPB_DUAL_RING) && !(PPB_EARLY_PROBE && !PPB_STAGE_INC), "option combinations");
 constexpr int kRings = PPB_DUAL_RING ? 2 : 1;
 constexpr int kAllStages = kRings * kStages;
 constexpr int kJJUnroll = PPB_JJ_UNROLL;           // column-loop unroll inside a stage
@@ -322,7 +338,7 @@ __device__ __forceinline__ bool store_pair(const QueryParams &p, double sy, doub
 }
 
 // generic path: any output mode, logs computed in place (also the fallback when the y-table would be huge)
-__device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32_t *cnt, int jl, int il,
+__device__ __forceinline__ bool pair_epilogue(const QueryParams &p, const uint32_t *cnt, int jl, int il,
                                               int64_t i, int64_t j, int64_t row, bool &degenerate) {
     const int K = p.K;
     const float *rt = nullptr;
@@ -331,7 +347,7 @@ __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32
     if (p.out_mode == PPB_OUT_COUNTS) {
         uint32_t *o = reinterpret_cast<uint32_t *>(p.out) + row * K;
         for (int t = 0; t < K; t++) o[t] = read_count(cnt, t, p.tj, jl, il);
-        return;
+        return false;
     }
     double sy = 0.0, sxy = 0.0;
     int n = 0;
@@ -353,11 +369,22 @@ __device__ __forceinline__ void pair_epilogue(const QueryParams &p, const uint32
             }
         }
     }
-    if (p.out_mode == PPB_OUT_JACCARD) return;
+    if (p.out_mode == PPB_OUT_JACCARD) return false;
     degenerate = n < 2;
-    (void)store_pair(p, sy, sxy, n, row);
+    return store_pair(p, sy, sxy, n, row);
 }
 
+
+// fused edge list: warp-aggregated append of the global row index of every pair on the within side (called by all 32 lanes)
+__device__ __forceinline__ void append_edge(const QueryParams &p, bool within, long long global_row, int lane) {
+    const uint32_t b = __ballot_sync(0xffffffffu, within);
+    if (b) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(p.edge_count, (unsigned long long)__popc(b));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(b & ((1u << lane) - 1));
+        if (within && at < (unsigned long long)p.edge_cap) p.edge_rows[at] = global_row;
+    }
+}
 
 // Epilogue of one tile, run by the kEpiWarps epilogue warps (et = 0..95).  Work unit = 4 consecutive rows x
 // 32 column slots (lane = column: coalesced 256-B row-order stores); the 4 rows' counts of one k are one LDS.64.
@@ -436,15 +463,7 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
                     within = store_pair(p, sy[r], sxy[r], n[r], row);
                     n_deg += n[r] < 2;
                 }
-                if (p.edge_mode) {  // warp-aggregated append of the global row index
-                    const uint32_t b = __ballot_sync(0xffffffffu, within);
-                    if (b) {
-                        unsigned long long at = 0;
-                        if (lane == 0) at = atomicAdd(p.edge_count, (unsigned long long)__popc(b));
-                        at = __shfl_sync(0xffffffffu, at, 0) + __popc(b & ((1u << lane) - 1));
-                        if (within && at < (unsigned long long)p.edge_cap) p.edge_rows[at] = row + p.row_begin;
-                    }
-                }
+                if (p.edge_mode) append_edge(p, within, row + p.row_begin, lane);
             }
         } else {
             for (int r = 0; r < 4; r++) {
@@ -452,9 +471,10 @@ __device__ __forceinline__ void tile_epilogue(const QueryParams &p, const uint32
                 const long long row = ri.row_base + j;
                 const bool ok = ri.i_ok && j_ok && (!p.self || (i0 + il0 + r) < j) && row >= 0 &&
                                 row < p.row_end - p.row_begin;
-                bool deg = false;
-                if (ok) pair_epilogue(p, cnt, jl, il0 + r, i0 + il0 + r, j, row, deg);
+                bool deg = false, within = false;
+                if (ok) within = pair_epilogue(p, cnt, jl, il0 + r, i0 + il0 + r, j, row, deg);
                 n_deg += deg;
+                if (p.edge_mode) append_edge(p, within, row + p.row_begin, lane);   // outside the divergent branch
             }
         }
     }
@@ -610,6 +630,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
+#if PPB_STAGE_INC
+    // ring position of the NEXT stage to consume, kept incrementally: stage index, its full-barrier address, its data
+    // address and the parity to wait for
+    const uint32_t full0 = smem_u32(full), stage0 = smem_u32(stage_base);
+    uint32_t rs = 0, rbar = full0, rdat = stage0, rph = 0, rready = 0;
+#endif
 #if PPB_DUAL_RING
     const uint32_t ring_base = (uint32_t)(warp >> 2) * kStages;           // warps 0-3: ring 0, warps 4-7: ring 1
     const int ks_shift = (warp >> 2) * (p.K / 2) * p.n_slices;            // the second group starts half-way round the k's
@@ -629,6 +655,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         mbar_wait(&cempty[cb], cph ^ 1);  // the epilogue warps are done with this count tile (2 tiles ago)
 
         uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;  // packed (2 x uint16) partial counts of the previous column
+#if PPB_DEFER_PACK
+        uint32_t q4 = 0, q5 = 0, q6 = 0, q7 = 0;      // ... whose second half is still unpacked
+#endif
         uint32_t pdst = trash_addr, pacc = 0;          // where they go; whether they add to an earlier slice
 
 #if PPB_DUAL_RING
@@ -660,6 +689,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
             const uint32_t cnt_k = cnt_addr + k * tj * kCntRowWords * 4;
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
+#if PPB_STAGE_INC
+                if (!rready) mbar_wait_addr(rbar, rph);
+                const uint32_t sdat = rdat, sempty = rbar + kAllStages * 8;
+                // advance to the next stage now: its address is ready long before the next wait needs it
+                rbar += 8, rdat += kStageBytes;
+                if (++rs == kStages) rs = 0, rbar = full0, rdat = stage0, rph ^= 1;
+                rready = 0;
+#else
 #if PPB_DUAL_RING
                 const uint32_t s = ring_base + it % kStages, ph = (it / kStages) & 1;
 #else
@@ -667,14 +704,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
 #endif
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
+#endif
                 uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
 #pragma unroll kJJUnroll
                 for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
                     uint4 old = make_uint4(0u, 0u, 0u, 0u);
                     if (!kSingleSlice) old = lds128(pdst);  // what earlier slices of this k stored for the previous column
+#if PPB_EARLY_PROBE
+                    if (jj == kJB - 1) rready = mbar_test_addr(rbar, rph);  // next stage: usually already there
+#endif
+#if PPB_STAGE_INC
+                    const uint32_t cb = sdat + jj * kSliceBytes + lane * 16;
+                    const uint4 b0 = lds128(cb), b1 = lds128(cb + 512), b2 = lds128(cb + 1024);
+                    const uint2 b3 = lds64(sdat + jj * kSliceBytes + 1536 + lane * 8);
+#else
                     const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + jj * kSliceBytes);
                     const uint4 b0 = b4[lane], b1 = b4[32 + lane], b2 = b4[64 + lane];
                     const uint2 b3 = reinterpret_cast<const uint2 *>(sb + jj * kSliceBytes + 1536)[lane];
+#endif
                     const uint32_t bw[kBbits] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z,
                                                  b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y};
                     uint32_t c[kRowsPerWarp];
@@ -691,6 +738,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                         }
                         c[0] = __popc(x0), c[1] = __popc(x1), c[2] = __popc(x2), c[3] = __popc(x3);
                     }
+#if PPB_DEFER_PACK
+                    pk2 = pack2(q4, q5), pk3 = pack2(q6, q7);  // the previous column's second half: its POPCs are long done
+#endif
                     // previous column: warp-sum of its packed counts (inputs were ready an iteration ago)
                     const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
                     {
@@ -706,15 +756,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                     }
                     store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
                     // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
-                    pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]), pk2 = pack2(c[4], c[5]), pk3 = pack2(c[6], c[7]);
+                    pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]);
+#if PPB_DEFER_PACK
+                    q4 = c[4], q5 = c[5], q6 = c[6], q7 = c[7];
+#else
+                    pk2 = pack2(c[4], c[5]), pk3 = pack2(c[6], c[7]);
+#endif
                     pdst = dst;
                     pacc = sl;
                 }
                 __syncwarp();
+#if PPB_STAGE_INC
+                if (lane == 0) mbar_arrive_addr(sempty);
+#else
                 if (lane == 0) mbar_arrive(&empty[s]);
+#endif
             }
         }
         {  // drain the pipeline: the tile's last column
+#if PPB_DEFER_PACK
+            pk2 = pack2(q4, q5), pk3 = pack2(q6, q7);
+#endif
             const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
             uint4 old = make_uint4(0u, 0u, 0u, 0u);
             if (!kSingleSlice) old = lds128(pdst);
@@ -781,6 +843,68 @@ __global__ void __launch_bounds__(256, 2) microbench_kernel(int64_t iters, uint3
 #pragma unroll
     for (int g = 0; g < 8; g++) acc ^= x[g];
     if (acc == 0x12345678u) sink[0] = acc;  // keep the work alive
+}
+
+
+// The compute warps' column body as a stand-alone loop (no barriers, no TMA, no epilogue warps): 8 register-stationary
+// rows x 14 planes, per column 3 LDS.128 + 1 LDS.64, 112 LOP3 in four interleaved chains, 8 POPC, 4 IMAD packs,
+// 4 REDUX and one predicated STS.128 — launched with kRows-row tiles and W warps per scheduler.  It answers "what
+// fraction of the LOP3 pipe can THIS instruction mix reach with W in-order warps per scheduler", i.e. how much of the
+// distance kernel's gap to the LOP3-only peak is the mix itself and how much is synchronisation.
+template <int kRows, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) mixbench_kernel(int64_t iters, uint32_t *sink, uint32_t seed, int with_lds) {
+    extern __shared__ __align__(128) uint8_t msm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *cols = reinterpret_cast<uint32_t *>(msm);                 // 4 column slices (7 KB), shared by all warps
+    for (int w = threadIdx.x; w < 4 * kSliceWords; w += blockDim.x) cols[w] = seed * (w + 1) + blockIdx.x;
+    __syncthreads();
+    uint32_t a[kRows][kBbits];
+#pragma unroll
+    for (int g = 0; g < kRows; g++)
+#pragma unroll
+        for (int q = 0; q < kBbits; q++) a[g][q] = (seed ^ (blockIdx.x * 2654435761u)) + (g * 14 + q) * 0x85ebca6bu + threadIdx.x;
+    const uint32_t base = smem_u32(msm), trash = base + 4 * kSliceBytes + warp * 16;
+    uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;
+    uint32_t b_reg[kBbits];
+#pragma unroll
+    for (int q = 0; q < kBbits; q++) b_reg[q] = seed + q * 0x9e3779b9u + lane;
+    for (int64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            uint32_t bw[kBbits];
+            if (with_lds) {
+                const uint32_t cb = base + jj * kSliceBytes + lane * 16;
+                const uint4 b0 = lds128(cb), b1 = lds128(cb + 512), b2 = lds128(cb + 1024);
+                const uint2 b3 = lds64(base + jj * kSliceBytes + 1536 + lane * 8);
+                bw[0] = b0.x, bw[1] = b0.y, bw[2] = b0.z, bw[3] = b0.w, bw[4] = b1.x, bw[5] = b1.y, bw[6] = b1.z;
+                bw[7] = b1.w, bw[8] = b2.x, bw[9] = b2.y, bw[10] = b2.z, bw[11] = b2.w, bw[12] = b3.x, bw[13] = b3.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kBbits; q++) bw[q] = b_reg[q] + pk0;  // keeps the values loop-variant
+            }
+            uint32_t c[kRows];
+#pragma unroll
+            for (int h = 0; h < kRows; h += 4) {
+                uint32_t x0 = 0xffffffffu, x1 = 0xffffffffu, x2 = 0xffffffffu, x3 = 0xffffffffu;
+#pragma unroll
+                for (int q = 0; q < kBbits; q++) {
+                    x0 = and_xnor(x0, a[h][q], bw[q]);
+                    if (h + 1 < kRows) x1 = and_xnor(x1, a[h + 1][q], bw[q]);
+                    if (h + 2 < kRows) x2 = and_xnor(x2, a[h + 2][q], bw[q]);
+                    if (h + 3 < kRows) x3 = and_xnor(x3, a[h + 3][q], bw[q]);
+                }
+                c[h] = __popc(x0);
+                if (h + 1 < kRows) c[h + 1] = __popc(x1);
+                if (h + 2 < kRows) c[h + 2] = __popc(x2);
+                if (h + 3 < kRows) c[h + 3] = __popc(x3);
+            }
+            const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
+            store_counts<false>(trash, r0, r1, r2, r3, lane, 0, make_uint4(0, 0, 0, 0));
+            pk0 = pack2(c[0], c[1 % kRows]), pk1 = pack2(c[2 % kRows], c[3 % kRows]);
+            pk2 = pack2(c[4 % kRows], c[5 % kRows]), pk3 = pack2(c[6 % kRows], c[7 % kRows]);
+        }
+    }
+    if ((pk0 ^ pk1 ^ pk2 ^ pk3) == 0x12345678u) sink[0] = pk0;
 }
 
 }  // namespace ppb

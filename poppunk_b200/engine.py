@@ -52,10 +52,24 @@ class PackedSketches:
     K: int
     sketchsize64: int
     clusters: Optional[torch.Tensor] = None   # uint16-as-int16 [n] random-match cluster ids
+    max_cluster: int = -1                     # largest cluster id (checked against the table size at query time)
 
     @property
     def device(self):
         return self.data.device
+
+
+@dataclass
+class DeviceClusters:
+    """Random-match cluster ids that already live on the device (uint16 bit patterns in an int16 tensor), with their
+    maximum known on the host — what a caller that packs repeatedly hands to :func:`pack` instead of a NumPy array."""
+    ids: torch.Tensor
+    max_id: int
+
+    @staticmethod
+    def upload(clusters, device) -> "DeviceClusters":
+        cl_np = np.ascontiguousarray(clusters, dtype=np.uint16)
+        return DeviceClusters(torch.from_numpy(cl_np.view(np.int16)).to(device), int(cl_np.max()) if cl_np.size else -1)
 
 
 def as_device_sketches(sketches, device=None) -> torch.Tensor:
@@ -94,11 +108,18 @@ def pack(sketches, idx=None, clusters=None, device=None) -> PackedSketches:
         check(L.ppb_pack_dev(sk.data_ptr(), n_src, idx_t.data_ptr() if idx_t is not None else None, n, K, ss64,
                              out.data_ptr(), _stream_ptr(dev)), "ppb_pack_dev")
     cl = None
+    if isinstance(clusters, DeviceClusters):      # already resident (list order): nothing to upload, nothing to wait for
+        if clusters.ids.numel() != n or clusters.ids.device != dev:
+            raise ValueError("one cluster id per packed genome, on the sketches' device")
+        return PackedSketches(out, n, K, ss64, clusters.ids, clusters.max_id)
     if clusters is not None:
         cl_np = np.ascontiguousarray(clusters, dtype=np.uint16)
         if idx is not None:
             cl_np = cl_np[np.asarray(idx, dtype=np.int64)]
+        if cl_np.shape != (n,):
+            raise ValueError("one cluster id per genome")
         cl = torch.from_numpy(cl_np.view(np.int16)).to(dev)
+        return PackedSketches(out, n, K, ss64, cl, int(cl_np.max()) if n else -1)
     return PackedSketches(out, n, K, ss64, cl)
 
 
@@ -149,6 +170,8 @@ def query(ref: PackedSketches, qry: Optional[PackedSketches], kmers: Sequence[in
             raise ValueError("random-match table must be [C][C][K]")
         if ref.clusters is None or (not self_mode and qry.clusters is None):
             raise ValueError("random-match table given but sketches carry no cluster ids")
+        if ref.max_cluster >= C_ or (not self_mode and qry.max_cluster >= C_):
+            raise ValueError("cluster id out of range for the random-match table (the kernel indexes the table with it)")
     if want_out and out is None:
         if out_mode == OUT_DISTS:
             out = torch.empty((rows, 2), dtype=torch.float32, device=dev)
@@ -357,6 +380,10 @@ def query_edges(ref: PackedSketches, qry: Optional[PackedSketches], kmers, bound
     if rand_table is not None:
         tab = torch.as_tensor(rand_table, dtype=torch.float32).to(dev).contiguous()
         C_ = tab.shape[0]
+        if ref.clusters is None or (not self_mode and qry.clusters is None):
+            raise ValueError("random-match table given but sketches carry no cluster ids")
+        if ref.max_cluster >= C_ or (not self_mode and qry.max_cluster >= C_):
+            raise ValueError("cluster id out of range for the random-match table")
     edge_rows = torch.empty(capacity, dtype=torch.int64, device=dev)
     n_edges = torch.zeros(1, dtype=torch.int64, device=dev)
     ndeg = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -421,6 +448,10 @@ class FusedExchange:
         if rand_table is not None:
             tab = torch.as_tensor(rand_table, dtype=torch.float32).to(dev).contiguous()
             C_ = tab.shape[0]
+            if ref.clusters is None or (not self_mode and qry.clusters is None):
+                raise ValueError("random-match table given but sketches carry no cluster ids")
+            if ref.max_cluster >= C_ or (not self_mode and qry.max_cluster >= C_):
+                raise ValueError("cluster id out of range for the random-match table")
         if n_degenerate is None:
             n_degenerate = torch.zeros(1, dtype=torch.int64, device=dev)
         peers = (C.c_void_p * self.world)(*self.peer_ptrs)

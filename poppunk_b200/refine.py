@@ -211,6 +211,17 @@ def _coo_to_device(rr_mat, dev):
             torch.as_tensor(np.ascontiguousarray(d, dtype=np.float32)).to(dev))
 
 
+KNN_MAX = 2048            # kKnnMax in csrc/ppb_refine.cuh: the survivors of a row are sorted in shared memory
+LOWER_RANK_MAX_ROW = 1024  # kLowerMaxRow: a sample's sparse row is sorted by one warp in shared memory
+
+
+def _check_knn(kNN, who):
+    """Limits the reference does not have ("Limits"): fail with a clear message, never a wrong result."""
+    if kNN < 0 or kNN > KNN_MAX:
+        raise ValueError(f"{who}(): kNN = {kNN} is outside this engine's range [0, {KNN_MAX}] "
+                         "(PopPUNK's lineage ranks are 1..~100; use the reference's CPU poppunk_refine beyond that)")
+
+
 def get_kNN_distances(distMat, kNN, dist_col=0, num_threads=1, device_id=0):
     """``poppunk_refine.get_kNN_distances`` (src/extend.cpp:245-289, bound at src/python_bindings.cpp:131-136):
     ``(i_vec, j_vec, dists)`` lists, ``rows * kNN`` long, of each row's nearest columns (ties: lower column first;
@@ -228,6 +239,9 @@ def get_kNN_distances(distMat, kNN, dist_col=0, num_threads=1, device_id=0):
         m = distMat.to(dev).contiguous()
     rows, cols = m.shape
     kNN = int(kNN)
+    if kNN == 0:
+        return [], [], []                                       # the reference's loops produce nothing
+    _check_knn(kNN, "get_kNN_distances")
     with torch.cuda.device(dev):
         oi = torch.empty(rows * kNN, dtype=torch.int64, device=dev)
         oj = torch.empty(rows * kNN, dtype=torch.int64, device=dev)
@@ -273,6 +287,9 @@ def extend(rr_mat, qq_mat, qr_mat, kNN, num_threads=1, device_id=0):
     L = _lib.load()
     nr, nq = qr_mat.shape
     kNN = int(kNN)
+    if kNN == 0:
+        return [], [], []
+    _check_knn(kNN, "extend")
     with torch.cuda.device(dev):
         si, sj, sd = _coo_to_device(rr_mat, dev)
         qq = torch.from_numpy(qq_mat).to(dev)

@@ -5,8 +5,10 @@ which is outside the hot path.  For parity tests and 
 sketch arrays with realistic, non-degenerate Jaccards: pure i.i.d. random signatures give
 J ~ 2^-14 < 5/S for every pair, i.e. every regression is truncated away (docs/sketching.rst:161-165).
 
-Model: a root signature table, ``n_lineages`` lineage tables derived from it and
-genomes derived from a lineage.  At each derivation step and for each k a bin keeps its parent's
+Model: ``n_roots`` independent ancestor signature tables, ``n_lineages`` lineage tables
+derived from them (round-robin) and genomes derived from a lineage.  Pairs under one ancestor are related
+(``E[J_k] ~ (1-a)(1-pi)^k``); pairs under different ancestors share only chance matches (J ~ 2^-14 < 5/S), so
+their series is truncated away and they come out as degenerate (0, 0) pairs — both paths of the fit are exercised.  At each derivation step and for each k a bin keeps its parent's
 signature with probability ``p_k = sqrt((1-a)(1-pi)^k)`` and is redrawn uniformly otherwise, so two
 genomes with a common parent have ``E[J_k] ~ (1-a)(1-pi)^k`` — the relation PopPUNK fits
 (PopPUNK/sketchlib.py:482).
@@ -60,7 +62,7 @@ def _derive(rng, parent, p_keep):
 
 
 def synth_signatures(n, kmers, sketchsize64, seed=42, n_lineages=8,
-                     pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=2048, sample_seed=0):
+                     pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=2048, sample_seed=0, n_roots=1):
     """Generator of ``(start, uint16 [m][K][S])`` signature chunks for ``n`` genomes.
 
     ``seed`` fixes the population (root + lineages); ``sample_seed`` fixes the genomes drawn from it, so
@@ -77,7 +79,12 @@ def synth_signatures(n, kmers, sketchsize64, seed=42, n_lineages=8,
         a = rng.uniform(*a_range, size=m)
         return np.sqrt((1.0 - a)[:, None] * (1.0 - pi)[:, None] ** kmers[None, :])  # [m][K]
 
-    lin = _derive(rng, np.broadcast_to(root, (n_lineages, K, S)), p_keep(n_lineages))
+    if n_roots <= 1:
+        parents = np.broadcast_to(root, (n_lineages, K, S))
+    else:   # lineage l descends from ancestor l % n_roots; ancestors are independent
+        roots = np.concatenate([root[None], rng.integers(0, 1 << BBITS, size=(n_roots - 1, K, S), dtype=np.uint16)])
+        parents = roots[np.arange(n_lineages) % n_roots]
+    lin = _derive(rng, parents, p_keep(n_lineages))
     rng = np.random.default_rng([seed, sample_seed])
     for start in range(0, n, chunk):
         m = min(chunk, n - start)
@@ -119,9 +126,10 @@ def synth_clusters(n, n_clusters=3, seed=42) -> np.ndarray:
 
 
 def synth_sketches_torch(n, kmers, sketchsize64, seed=42, device="cuda", n_lineages=8,
-                         pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=4096):
+                         pi_range=(0.001, 0.02), a_range=(0.01, 0.2), chunk=4096, n_roots=1, sample_seed=0):
     """Same population model as :func:`synth_sketches`, generated on ``device`` with torch (fast enough for
-    N = 100k).  Not bit-identical to the NumPy generator (different RNG) — bench.py uses it and hands the CPU
+    N = 100k).  ``seed`` fixes the population; a non-zero ``sample_seed`` draws OTHER genomes from it (query sets
+    related to a reference set of the same ``seed``).  Not bit-identical to the NumPy generator (different RNG) — bench.py uses it and hands the CPU
     baseline a device->host copy of the very same array.  Returns int64 ``[n][K][W]`` (uint64 bit patterns)."""
     import torch
     dev = torch.device(device)
@@ -141,7 +149,14 @@ def synth_sketches_torch(n, kmers, sketchsize64, seed=42, device="cuda", n_linea
         return torch.where(keep, parent, fresh)
 
     root = torch.randint(0, 1 << BBITS, (K, S), device=dev, dtype=torch.int16, generator=g)
-    lin = derive(root.expand(n_lineages, K, S), p_keep(n_lineages))
+    if n_roots <= 1:
+        parents = root.expand(n_lineages, K, S)
+    else:
+        more = torch.randint(0, 1 << BBITS, (n_roots - 1, K, S), device=dev, dtype=torch.int16, generator=g)
+        parents = torch.cat([root[None], more])[torch.arange(n_lineages, device=dev) % n_roots]
+    lin = derive(parents, p_keep(n_lineages))
+    if sample_seed:
+        g.manual_seed(1_000_003 * int(sample_seed) + seed)   # the population is fixed; these genomes are new draws from it
     weights = (torch.ones(64, dtype=torch.int64, device=dev) << torch.arange(64, device=dev))  # bin t -> bit t
     out = torch.empty((n, K, sketchsize64 * BBITS), dtype=torch.int64, device=dev)
     for start in range(0, n, chunk):

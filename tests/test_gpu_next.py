@@ -173,3 +173,42 @@ def test_refine_rest_vs_oracle_larger(eng, oracle):
     qq = np.round(rng.random((33, 33)), 2).astype(np.float32)
     for k in (1, 10, 40):
         assert refine.extend((ci, cj, cd), qq, qr, k) == _lists(oracle.extend(ci, cj, cd, qq, qr, k))
+
+
+def test_fused_query_edges_without_ytable(eng, oracle, monkeypatch):
+    """when the y-table is skipped (huge C*C*K*(S+1); forced here with PPB_NO_YTAB) the epilogue's generic
+    branch must append edges too, not silently return none."""
+    ref = synth.synth_sketches(400, KMERS, 16, seed=2)
+    tab, cl = synth.random_match_table(KMERS, 3), synth.synth_clusters(400, 3)
+    pr = eng.pack(ref, clusters=cl)
+    bnd = (2, 0.02, 0.2, 1.0, 1.0)
+    gi, gj, n, _ = eng.query_edges(pr, None, KMERS, bnd, rand_table=tab)
+    monkeypatch.setenv("PPB_NO_YTAB", "1")
+    si, sj, n_slow, _ = eng.query_edges(pr, None, KMERS, bnd, rand_table=tab)
+    assert n_slow == n > 0 and (si == gi).all() and (sj == gj).all()
+    _, lab_o, _ = oracle.query(ref, None, KMERS, tab, cl, boundary=bnd)
+    assert n_slow == int((lab_o == -1).sum())
+
+
+def test_empty_row_range_and_bad_cluster_ids(eng):
+    """an empty shard is a no-op (no "no output buffer" error: a rank with nothing to do must still reach
+    the collectives), and cluster ids outside the table are refused before they index it."""
+    import torch
+    ref = synth.synth_sketches(1, KMERS, 16, seed=2)
+    out, _, ndeg = eng.query(eng.pack(ref), None, KMERS)               # one genome: zero pairs
+    assert out.shape == (0, 2) and int(ndeg.item()) == 0
+    ref = synth.synth_sketches(50, KMERS, 16, seed=2)
+    pr = eng.pack(ref, clusters=np.full(50, 3, dtype=np.uint16))
+    out, _, _ = eng.query(pr, None, KMERS, row_begin=100, row_end=100)
+    assert out.shape == (0, 2)
+    with pytest.raises(ValueError):
+        eng.query(pr, None, KMERS, rand_table=synth.random_match_table(KMERS, 3))
+    torch.cuda.synchronize()
+
+
+def test_knn_zero_and_limits(eng):
+    from poppunk_b200 import refine
+    m = np.random.default_rng(0).random((20, 20)).astype(np.float32)
+    assert refine.get_kNN_distances(m, 0) == ([], [], [])
+    with pytest.raises(ValueError):
+        refine.get_kNN_distances(m, refine.KNN_MAX + 1)

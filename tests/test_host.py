@@ -279,3 +279,91 @@ def test_tile_schedule_covers_every_pair_once(lib, n_ref, n_qry, self_mode, tile
         i_hi = lib.ppb_calc_row_idx(e - 1, n_ref) if self_mode else (e - 1) // n_ref
         assert tiles[:, 0].min() == i_lo // 64 and tiles[:, 0].max() == i_hi // 64     # no row tile outside the shard
     assert lib.ppb_plan_tiles(n_ref, n_qry, int(self_mode), 0, total + 1, tile_cols, band, None, 0) == -1
+
+
+def test_device_shards_are_balanced_tile_aligned_and_cover(lib):
+    """ppb_plan_device_shards: what ppb_query_host_multi gives each device."""
+    import ctypes as C
+    for n_ref, n_qry, self_ in ((100_000, 0, 1), (50_000, 1_000_000, 0), (1000, 0, 1), (70, 33, 0)):
+        total = lib.ppb_num_rows(n_ref, n_qry, self_)
+        for G in (1, 2, 3, 8):
+            cuts = (C.c_int64 * (G + 1))()
+            assert lib.ppb_plan_device_shards(n_ref, n_qry, self_, 0, total, G, cuts) == G
+            cuts = list(cuts)
+            assert cuts[0] == 0 and cuts[-1] == total and all(a <= b for a, b in zip(cuts, cuts[1:]))
+            for c in cuts[1:-1]:      # interior cuts sit where a 64-genome row tile begins (or at the very end)
+                if c == total:
+                    continue
+                if self_:
+                    i = lib.ppb_calc_row_idx(c, n_ref)
+                    assert i % 64 == 0 and lib.ppb_square_to_condensed(i, i + 1, n_ref) == c
+                else:
+                    assert c % n_ref == 0 and (c // n_ref) % 64 == 0
+            if total > 50_000_000:
+                sizes = np.diff(cuts)
+                assert sizes.max() / sizes.min() < 1.02
+    sub = (C.c_int64 * 3)()
+    assert lib.ppb_plan_device_shards(1000, 0, 1, 1234, 400_000, 2, sub) == 2 and sub[0] == 1234 and sub[2] == 400_000
+    assert lib.ppb_plan_device_shards(1000, 0, 1, 0, 10**9, 2, sub) == -1
+
+
+def test_host_pool_without_gpu(lib):
+    """ppb_host_alloc / ppb_host_free: blocks are reused; without a CUDA device nothing is page-locked."""
+    import ctypes as C
+    from poppunk_b200 import engine
+    lib.ppb_release_workspace()
+    a = engine.host_result((1000, 2), np.float32)
+    a[:] = 3.0
+    addr = a.ctypes.data
+    del a
+    b = engine.host_result((999, 2), np.float32)
+    assert b.ctypes.data == addr and b.flags.writeable and b.flags.c_contiguous
+    h, u, p = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    lib.ppb_host_pool_stats(C.byref(h), C.byref(u), C.byref(p))
+    assert h.value == u.value == 2 << 20 and p.value == 0
+    assert lib.ppb_host_free(C.c_void_p(12345)) != 0          # not a pool block
+    del b
+    lib.ppb_release_workspace()
+    lib.ppb_host_pool_stats(C.byref(h), C.byref(u), C.byref(p))
+    assert h.value == 0
+    assert engine.host_result((0, 2), np.float32).shape == (0, 2)
+
+
+def test_random_match_fallback_formula():
+    """docs/sketching.rst:107-118: r = 1 - (1 - 2 4^-k)^l, J_r = r1 r2 / (r1 + r2 - r1 r2)."""
+    from poppunk_b200 import sketchlib
+    k = np.array([13, 17, 21], dtype=np.int32)
+    lens = np.array([2.0e6, 2.0e6, 3.1e6, 1.2e6])
+    tab, rcl, qcl = sketchlib.random_match_fallback(lens, lens[:2], k)
+    assert tab.shape == (3, 3, 3) and tab.dtype == np.float32 and qcl.tolist() == [rcl[0], rcl[1]]
+    assert rcl[0] == rcl[1] and len({int(c) for c in rcl}) == 3
+    r = 1.0 - (1.0 - 2.0 * 4.0 ** (-k.astype(np.float64))) ** 2.0e6
+    assert np.allclose(tab[rcl[0], rcl[0]], r * r / (2 * r - r * r), rtol=1e-6)     # the docs' equal-length form
+    single, _, _ = sketchlib.random_match_fallback(lens, None, k, use_rc=False)
+    r1 = 1.0 - (1.0 - 4.0 ** (-k.astype(np.float64))) ** 2.0e6
+    assert np.allclose(single[rcl[0], rcl[0]], r1 * r1 / (2 * r1 - r1 * r1), rtol=1e-6)
+    # many distinct lengths: at most 32 classes, every genome within ~its class's spread of the representative
+    rng = np.random.default_rng(0)
+    many = rng.uniform(1.8e6, 2.4e6, size=5000)
+    tab, cl, _ = sketchlib.random_match_fallback(many, None, k)
+    assert tab.shape[0] == 32 and np.bincount(cl).min() >= 5000 // 32
+    with pytest.raises(RuntimeError):
+        sketchlib.random_match_fallback(np.array([2e6, np.nan]), None, k)
+
+
+def test_fitKmerCurve_matches_the_reference_goldens(golden_dir):
+    """tests/golden/fit_kmer_curve.npz = PopPUNK/sketchlib.py:635-670 executed from the reference tree (scipy).
+    The drop-in's own fitKmerCurve (used by the --plot-fit probe) solves the same bounded problem in closed form:
+    it must land where scipy's trust-region iteration lands (scipy stops ~1e-5 short of an active bound)."""
+    from poppunk_b200 import sketchlib
+    g = np.load(os.path.join(golden_dir, "fit_kmer_curve.npz"))
+    worst_inside = worst = 0.0
+    for r in range(len(g["n_k"])):
+        n = int(g["n_k"][r])
+        got = sketchlib.fitKmerCurve(g["jaccard"][r, :n], g["klist"][r, :n])
+        exp = g["expected"][r]
+        err = float(np.abs(got - exp).max())
+        worst = max(worst, err)
+        if exp.min() > 0.003:
+            worst_inside = max(worst_inside, err)
+    assert worst_inside < 1e-6 and worst < 2e-4

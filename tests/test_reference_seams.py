@@ -114,6 +114,47 @@ def test_read_db_reads_what_the_reference_writer_writes(tmp_path, monkeypatch, g
     assert sub.names == ["sampleB"] and sub.sketches.shape[0] == 1
 
 
+def test_read_db_reads_the_random_group(tmp_path, monkeypatch):
+    """The HDF5 branch of read_db picks up ``/random`` (object names [UPSTREAM-RECALL]: pp-sketchlib's writer is not in
+    the reference tree — PopPUNK only copies the group between files, sketchlib.py:278-279, 321-322) and the per-sample
+    ``length`` / ``base_freq`` attrs (web.py:33-61); samples the table does not list get the nearest centroid."""
+    from poppunk_b200 import sketchlib, synth
+    fake = FakeH5py()
+    prefix = str(tmp_path / "db")
+    os.makedirs(prefix)
+    kmers = np.array([13, 17, 21], dtype=np.int32)
+    sk = synth.synth_sketches(4, kmers, 2, seed=9)
+    names = ["a", "b", "c", "d"]
+    centroids = np.array([[0.3, 0.2, 0.2, 0.3], [0.2, 0.3, 0.3, 0.2]])
+    f = fake.File(os.path.join(prefix, "db.h5"), "w")
+    grp = f.create_group("sketches")
+    grp.attrs["sketch_version"], grp.attrs["codon_phased"] = "x", False
+    for i, n in enumerate(names):
+        g = grp.create_group(n)
+        g.attrs.update(kmers=list(kmers), sketchsize64=2, bbits=14, length=2_000_000 + i,
+                       base_freq=list(centroids[i % 2]), missing_bases=0)
+        for t, k in enumerate(kmers):
+            g.create_dataset(str(int(k)), data=sk[i, t], dtype="u8")
+    rnd = f.create_group("random")
+    rnd.attrs.update(k_min=13, k_max=21, use_rc=True)
+    rnd.create_dataset("table_keys", data=np.array([b"a", b"b", b"c"]))      # 'd' was added later, without addRandom
+    rnd.create_dataset("table_values", data=np.array([0, 1, 1], dtype=np.uint16))
+    per_k = np.stack([np.array([[0.03, 0.02], [0.02, 0.01]]) / (10 ** t) for t in range(3)])   # [K][C][C], symmetric
+    rnd.create_dataset("matches_keys", data=kmers.astype(np.uint64))
+    rnd.create_dataset("matches_values", data=per_k.ravel())
+    rnd.create_dataset("centroids", data=centroids)
+    monkeypatch.setattr(sketchlib, "h5py", fake)
+    db = sketchlib.read_db(prefix, ["d", "a", "c"])
+    assert db.names == ["d", "a", "c"] and (db.sketches == sk[[3, 0, 2]]).all()
+    assert db.random_table.shape == (2, 2, 3) and np.allclose(db.random_table[..., 1], per_k[1])
+    assert db.random_clusters.tolist() == [0xFFFF, 0, 1] and db.lengths.tolist() == [2_000_003, 2_000_000, 2_000_002]
+    table, rcl, qcl = sketchlib.random_match_setup(db, np.arange(3), None, None, [17, 21])
+    assert table.shape == (2, 2, 2) and np.allclose(table[..., 0], per_k[1]) and qcl is None
+    assert rcl.tolist() == [1, 0, 1]                                        # 'd': base_freq == centroid 1
+    with pytest.raises(RuntimeError):
+        sketchlib.random_match_setup(db, np.arange(3), None, None, [13, 15])   # k = 15 is not in the database
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (not on the GPU box)")
 def test_wrapper_forwards_like_the_reference_wrapper(monkeypatch, capsys):
     """PopPUNK/sketchlib.py:475-632 ``queryDatabase`` (extracted from the reference tree, its ``pp_sketchlib`` replaced by

@@ -67,6 +67,7 @@ int main(int argc, char **argv) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (argc > 2) ndev = std::min(ndev, atoi(argv[2]));
+    const bool quick = argc > 3 && std::string(argv[3]) == "quick";  // multi-GPU boxes are charged per GPU: the essentials only
     const size_t bytes = (size_t)(gib_arg * (double)((size_t)1 << 30));
     const double GB = 1e9;
     const int hw = (int)std::thread::hardware_concurrency();
@@ -126,8 +127,8 @@ int main(int argc, char **argv) {
     // ---- fresh pageable memory: first touch, memcpy from pinned, cudaHostRegister, driver-staged D2H
     CK(cudaSetDevice(0));
     for (int huge = 0; huge <= 1; huge++) {
-        for (int T : {1, 4, 8, 16, 32}) {
-            if (T > 2 * hw) continue;
+        for (int T : {1, 4, 8, 16, 32, 64}) {
+            if (T > 2 * hw || (quick && T != 8 && T != 16 && T != hw)) continue;
             void *p = fresh(bytes, huge);
             double t0 = now();
             par(T, bytes, [&](size_t off, size_t len) {
@@ -147,7 +148,7 @@ int main(int argc, char **argv) {
                         huge, T, bytes / touch / GB, bytes / warm / GB, bytes / cold / GB);
             std::fflush(stdout);
         }
-        {   // cudaHostRegister of fresh / touched memory, then D2H straight into it
+        if (!quick) {   // cudaHostRegister of fresh / touched memory, then D2H straight into it
             void *p = fresh(bytes, huge);
             double t0 = now();
             cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
@@ -185,7 +186,7 @@ int main(int argc, char **argv) {
                         huge, bytes / reg_fresh / GB, bytes / reg_touched / GB, bytes / reg_chunks / GB, bytes / unreg / GB, d2h, e == cudaSuccess);
             std::fflush(stdout);
         }
-        {   // the driver's own staging: cudaMemcpy D2H into fresh pageable memory
+        if (!quick) {   // the driver's own staging: cudaMemcpy D2H into fresh pageable memory
             void *p = fresh(bytes, huge);
             double t0 = now();
             CK(cudaMemcpy(p, d_buf[0], bytes, cudaMemcpyDeviceToHost));
@@ -200,9 +201,9 @@ int main(int argc, char **argv) {
         }
     }
     // ---- the pipelined staged path as ppb_query_host runs it: D2H into a pinned ring while T threads drain it into fresh pages
-    for (int huge = 0; huge <= 1; huge++)
-        for (int T : {4, 8, 16}) {
-            if (T > hw) continue;
+    for (int huge = quick ? 1 : 0; huge <= 1; huge++)
+        for (int T : {4, 8, 16, 32}) {
+            if (T > hw || (quick && T < 16)) continue;
             void *p = fresh(bytes, huge);
             const size_t piece = (size_t)128 << 20;
             const int ring = 4;
