@@ -81,6 +81,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.proc = None
         self.path = f"/tmp/ppb_clocks_{os.getpid()}.csv"
+        if os.environ.get("PPB_BENCH_NO_SAMPLER"):
+            return
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(
@@ -290,8 +292,12 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # CPU-side meeting point for the e2e leg: while rank 0 drives every GPU from ONE process, the other ranks must not
+        # sit in an NCCL barrier (its kernel spins on their GPU and would time-slice with rank 0's work there)
+        host_group = dist.new_group(backend="gloo")
     L = _lib.load()
 
     n = args.n
@@ -329,12 +335,16 @@ def run_gpu(args):
             step()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         n0 = L.ppb_launch_count()
         ev0.record()
-        for _ in range(steps):
+        for i in range(steps):
             step()
+            marks[i].record()
         ev1.record()
         barrier()
+        if rank == 0:
+            log("[bench] step times (ms): " + ", ".join(f"{a.elapsed_time(b_):.1f}" for a, b_ in zip([ev0] + marks[:-1], marks)))
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -495,6 +505,8 @@ def run_gpu(args):
         del ex
     torch.cuda.empty_cache()
     barrier()
+    if host_group is not None:
+        dist.barrier(group=host_group)      # everybody's GPU is idle and stays idle: the others now wait on a socket
     e2e = None
     floor = None
     if rank == 0:
@@ -547,6 +559,8 @@ def run_gpu(args):
         except Exception as err:  # e.g. the box cannot hold two 40 GB host blocks
             log(f"[bench] e2e leg failed: {err!r}")
             e2e = {"value": None, "unit": UNIT, "error": repr(err)[:300]}
+    if host_group is not None:
+        dist.barrier(group=host_group)
     barrier()
 
     if rank != 0:

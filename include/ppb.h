@@ -166,6 +166,9 @@ int ppb_query_edges_dev(const uint32_t *d_ref_packed, int64_t n_ref,
                         unsigned long long *d_n_degenerate, void *stream);
 int ppb_rows_to_pairs_dev(const int64_t *d_rows, int64_t n, int32_t self, int64_t n_samples_or_num_ref,
                           int64_t int_offset, int64_t *d_i, int64_t *d_j, void *stream);
+/* Ascending in-place sort of n row indices in [0, max_row] (what brings ppb_query_edges_dev's unordered rows into the
+ * reference's row order): least-significant-digit radix sort, 8 bits per pass, hand-written (csrc/ppb_sort.cuh).   */
+int ppb_sort_rows_dev(int64_t *d_rows, int64_t n, int64_t max_row, void *stream);
 size_t ppb_edges_scratch_bytes(int64_t n_rows);
 int ppb_edges_from_dists_dev(const float *d_dists, int64_t n_rows, int64_t n_samples, int32_t slope,
                              float x_max, float y_max, int64_t *d_i, int64_t *d_j, int64_t capacity,

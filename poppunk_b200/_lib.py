@@ -22,7 +22,7 @@ SYMBOLS = [
     "ppb_square_to_long_dev", "ppb_long_to_square_multi_dev", "ppb_plan_host_chunks",
     "ppb_generate_all_tuples_dev", "ppb_threshold_iterate_1d_dev", "ppb_threshold_iterate_2d_dev", "ppb_knn_dev",
     "ppb_lower_rank_dev", "ppb_extend_dev", "ppb_plan_tiles", "ppb_pack_part_dev", "ppb_query_host_multi",
-    "ppb_plan_device_shards", "ppb_host_alloc", "ppb_host_free", "ppb_host_pool_stats", "ppb_microbench_mix_dev",
+    "ppb_plan_device_shards", "ppb_host_alloc", "ppb_host_free", "ppb_host_pool_stats", "ppb_microbench_mix_dev", "ppb_sort_rows_dev",
 ]
 
 
@@ -94,6 +94,8 @@ def load():
     L.ppb_query_edges_dev.restype = C.c_int
     L.ppb_rows_to_pairs_dev.argtypes = [vp, i64, i32, i64, i64, vp, vp, vp]
     L.ppb_rows_to_pairs_dev.restype = C.c_int
+    L.ppb_sort_rows_dev.argtypes = [vp, i64, i64, vp]
+    L.ppb_sort_rows_dev.restype = C.c_int
     L.ppb_edges_scratch_bytes.argtypes = [i64]
     L.ppb_edges_scratch_bytes.restype = C.c_size_t
     L.ppb_edges_from_dists_dev.argtypes = [vp, i64, i64, i32, f32, f32, vp, vp, i64, vp, vp, vp]

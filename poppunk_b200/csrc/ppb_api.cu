@@ -15,11 +15,10 @@
 #include <tuple>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "ppb_kernels.cuh"
 #include "ppb_next.cuh"
 #include "ppb_refine.cuh"
+#include "ppb_sort.cuh"
 
 namespace {
 
@@ -251,8 +250,10 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     const int self = d_qry_packed == nullptr;
     if (!d_ref_packed || !kmers || K < 1 || K > PPB_MAX_K || n_ref < 0 || (!self && n_qry < 0))
         return fail(PPB_ERR_ARG, "ppb_query_dev: bad argument");
-    if (sketchsize64 < 1 || sketchsize64 > 1023)
-        return fail(PPB_ERR_ARG, "ppb_query_dev: sketchsize64 must be in [1, 1023] (uint16 per-k counts)");
+    if (sketchsize64 < 1 || sketchsize64 > (1 << 24))
+        return fail(PPB_ERR_ARG, "ppb_query_dev: sketchsize64 must be in [1, 2^24]");
+    const bool wide = sketchsize64 > 1023;   // more than 65535 bins: per-k counts no longer fit uint16 (PopPUNK accepts
+                                             // --sketch-size up to 10^6 bins, __main__.py:310)
     if (out_mode < PPB_OUT_DISTS || out_mode > PPB_OUT_COUNTS) return fail(PPB_ERR_ARG, "ppb_query_dev: bad out_mode");
     {   // an empty row range is a no-op whatever the buffers are (torch hands out null pointers for empty tensors, and
         // a rank with an empty shard must still reach the collectives that follow)
@@ -337,12 +338,13 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     int max_smem = 0, sm_smem = 0;
     PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     PPB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    auto smem_need = [&](int tjv) { return (size_t)ppb::smem_layout(K, tjv).total; };
+    auto smem_need = [&](int tjv) { return (size_t)ppb::smem_layout(K, tjv, wide).total; };
     const size_t per_cta_budget = std::min<size_t>((size_t)max_smem, (size_t)sm_smem / ppb::kCtasPerSM - 1024);
     int tj = ppb::kMaxTJ;
     while (tj > ppb::kJB && smem_need(tj) > per_cta_budget) tj >>= 1;
     if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
     p.tj = tj;
+    p.wide = wide;
 
     const size_t genome_bytes = (size_t)p.KS * ppb::kSliceBytes;
     int band = (int)std::min<size_t>(4096, std::max<size_t>(2, kBandBytes / (genome_bytes * ppb::kTI)));
@@ -382,16 +384,18 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
         static std::map<int, bool> attr_done;
         std::lock_guard<std::mutex> lk(attr_mu);
         if (!attr_done[dev]) {
-            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PPB_CUDA(cudaFuncSetAttribute(ppb::query_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr_done[dev] = true;
         }
     }
     // y-table for the fused fit (stream-ordered scratch; skipped when it would be unreasonably large)
     double *d_ytab = nullptr;
-    if (out_mode == PPB_OUT_DISTS) {
+    if (out_mode == PPB_OUT_DISTS && !wide) {   // (the fused fit reads uint16 counts: huge sketches take the generic epilogue)
         const size_t entries = (size_t)(d_rand_table ? (size_t)n_clusters * n_clusters : 1) * K * ((size_t)p.S + 1);
         YtabLease *lease = g_ytab_lease;
         if (lease && lease->buf && lease->capacity >= entries) {
@@ -416,9 +420,11 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     }
     const unsigned grid = (unsigned)std::min<int64_t>(tl.n, (int64_t)ppb::kCtasPerSM * sms);
     if (single)
-        ppb::query_kernel<true><<<grid, ppb::kThreads, smem, st>>>(p);
+        ppb::query_kernel<0><<<grid, ppb::kThreads, smem, st>>>(p);
+    else if (!wide)
+        ppb::query_kernel<1><<<grid, ppb::kThreads, smem, st>>>(p);
     else
-        ppb::query_kernel<false><<<grid, ppb::kThreads, smem, st>>>(p);
+        ppb::query_kernel<2><<<grid, ppb::kThreads, smem, st>>>(p);
     g_launches++;
     PPB_CUDA(cudaGetLastError());
     if (d_ytab) PPB_CUDA(cudaFreeAsync(d_ytab, st));
@@ -478,13 +484,17 @@ int run_select(Pred pred, int64_t n_rows, ppb::PairMap map, int64_t *d_i, int64_
         PPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
         return PPB_OK;
     }
-    const int64_t blocks = (n_rows + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
-    if (blocks > 0x7fffffff) return fail(PPB_ERR_ARG, "edge compaction: too many rows for one call");
-    int64_t *block_off = (int64_t *)d_scratch;
-    ppb::select_kernel<Pred><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(pred, n_rows, map, 0, block_off, capacity, d_i, d_j);
-    ppb::scan_kernel<<<1, 1024, 0, st>>>(block_off, blocks, d_count);
-    ppb::select_kernel<Pred><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(pred, n_rows, map, 1, block_off, capacity, d_i, d_j);
-    g_launches += 3;
+    // the input is read once: mark (bit per row + count per 1024-row unit) -> scan -> emit from the bit mask
+    const int64_t units = (n_rows + ppb::kUnitRows - 1) / ppb::kUnitRows;
+    uint32_t *bits = (uint32_t *)d_scratch;
+    uint32_t *unit_count = bits + units * 32;
+    int64_t *unit_off = (int64_t *)(unit_count + ((units + 1) & ~(int64_t)1));
+    const unsigned grid = (unsigned)std::min<int64_t>((units + 7) / 8, 148 * 16);
+    ppb::select_mark_kernel<Pred><<<grid, 256, 0, st>>>(pred, n_rows, bits, unit_count);
+    ppb::unit_scan_kernel<<<1, 1024, 0, st>>>(unit_count, units, unit_off, d_count);
+    ppb::select_emit_kernel<ppb::OutPairs><<<grid, 256, 0, st>>>(bits, unit_count, unit_off, n_rows, ppb::OutPairs{map, d_i, d_j}, capacity);
+    g_launches += 2;
+    g_launches++;
     PPB_CUDA(cudaGetLastError());
     return PPB_OK;
 }
@@ -492,7 +502,8 @@ int run_select(Pred pred, int64_t n_rows, ppb::PairMap map, int64_t *d_i, int64_
 }  // extern "C++"
 
 size_t ppb_edges_scratch_bytes(int64_t n_rows) {
-    return (size_t)((std::max<int64_t>(n_rows, 1) + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows) * sizeof(int64_t);
+    const size_t units = (size_t)((std::max<int64_t>(n_rows, 1) + ppb::kUnitRows - 1) / ppb::kUnitRows);
+    return units * 128 + (units + 2) * 4 + (units + 1) * 8;   // bit mask + unit counts + unit offsets
 }
 
 int ppb_rows_to_pairs_dev(const int64_t *d_rows, int64_t n, int32_t self, int64_t n_samples_or_num_ref,
@@ -644,8 +655,66 @@ void iterate_1d_boundary(double offset, int slope, float x0, float y0, float x1,
         *y_max = yi;
     }
 }
+// bisection over the boundaries is allowed when they move outward: positive, non-decreasing intercepts (csrc/ppb_next.cuh)
+ppb::StepSearch make_step_search(const float2 *d_step, const float2 *h_step, int n_off, int slope) {
+    ppb::StepSearch S;
+    S.step = d_step;
+    S.n_off = n_off;
+    S.slope = slope;
+    S.bisect = n_off >= 2 && !std::getenv("PPB_NO_BISECT");
+    S.XM = S.YM = 0.0f;
+    for (int o = 0; o < n_off; o++) {
+        const float x = h_step[o].x, y = h_step[o].y;
+        S.XM = std::max(S.XM, std::fabs(x));
+        S.YM = std::max(S.YM, std::fabs(y));
+        if (slope == 2 && !(x > 0.0f && y > 0.0f)) S.bisect = 0;            // degenerate / inward boundary: full scan
+        if (o > 0) {
+            if (slope != 1 && !(x >= h_step[o - 1].x)) S.bisect = 0;
+            if (slope != 0 && !(y >= h_step[o - 1].y)) S.bisect = 0;
+        }
+    }
+    return S;
+}
+
+// One pass of the least-significant-digit radix sort (8-bit digit at `shift`): count per chunk, scans, stable emit.
+// hist: int64 [chunks][256], totals / base: int64 [256].
+template <typename Digit, typename Move>
+int radix_pass(Digit dg, Move mv, int64_t n, int64_t *hist, int64_t *totals, int64_t *base, cudaStream_t st) {
+    const int64_t chunks = (n + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+    ppb::bucket_count_kernel<Digit><<<(unsigned)chunks, ppb::kSelThreads, 0, st>>>(dg, n, 256, hist);
+    ppb::bucket_scan_chunks_kernel<<<256, 1024, 0, st>>>(hist, chunks, 256, totals);
+    ppb::bucket_scan_totals_kernel<<<1, ppb::kBktMax, 0, st>>>(totals, 256, base, nullptr);
+    ppb::bucket_emit_kernel<Digit, Move><<<(unsigned)chunks, ppb::kSelThreads, 0, st>>>(dg, mv, n, 256, hist, base, INT64_MAX);
+    g_launches += 4;
+    PPB_CUDA(cudaGetLastError());
+    return PPB_OK;
+}
 }  // namespace
 }  // extern "C++"
+
+int ppb_sort_rows_dev(int64_t *d_rows, int64_t n, int64_t max_row, void *stream) {
+    if (n < 0 || max_row < 0 || (n > 0 && !d_rows)) return fail(PPB_ERR_ARG, "ppb_sort_rows_dev: bad argument");
+    if (n < 2) return PPB_OK;
+    if (n > ((int64_t)1 << 42)) return fail(PPB_ERR_ARG, "ppb_sort_rows_dev: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(st);
+    unsigned long long *tmp = nullptr;
+    int64_t *hist = nullptr, *tb = nullptr;
+    const int64_t chunks = (n + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+    if (int rc = sc.get(&tmp, (size_t)n)) return rc;
+    if (int rc = sc.get(&hist, (size_t)chunks * 256)) return rc;
+    if (int rc = sc.get(&tb, 512)) return rc;
+    int bits = 1;
+    while (bits < 63 && (max_row >> bits)) bits++;
+    int passes = (bits + 7) / 8;
+    if (passes & 1) passes++;  // an even number of passes leaves the result in the caller's buffer
+    unsigned long long *a = (unsigned long long *)d_rows, *b = tmp;
+    for (int ps = 0; ps < passes; ps++) {
+        if (int rc = radix_pass(ppb::DigitOfU64{a, ps * 8}, ppb::MoveKey64{a, b}, n, hist, tb, tb + 256, st)) return rc;
+        std::swap(a, b);
+    }
+    return PPB_OK;
+}
 
 int ppb_generate_all_tuples_dev(int64_t num_ref, int64_t num_queries, int32_t self, int64_t int_offset, int64_t *d_i,
                                 int64_t *d_j, void *stream) {
@@ -680,6 +749,37 @@ int ppb_threshold_iterate_2d_dev(const float *d_dists, int64_t n_rows, const flo
     float *d_x = nullptr;
     int64_t *cnt = nullptr;
     if (int rc = sc.get(&d_x, (size_t)n_off)) return rc;
+    if (n_off <= 64 && !std::getenv("PPB_ITERATE2D_GENERIC")) {
+        // what PopPUNK asks for (20-40 steps, refine.py:116-123,190-191): ONE read of the distances.  The classify
+        // pass leaves a byte per row (its admitting step), a stable bucket scatter by step places the rows.
+        uint8_t *note = nullptr;
+        int64_t *hist = nullptr, *tb = nullptr;
+        float2 *d_step = nullptr;
+        if (int rc = sc.get(&note, (size_t)n_rows)) return rc;
+        if (int rc = sc.get(&hist, (size_t)blocks * n_off)) return rc;
+        if (int rc = sc.get(&tb, 2 * ppb::kBktMax)) return rc;
+        if (int rc = sc.get(&d_step, 64)) return rc;
+        float2 h_step[64];
+        for (int o = 0; o < n_off; o++) h_step[o] = make_float2(x_max[o], x_max[o] * y_max);  // float product, as line_dist forms it
+        PPB_CUDA(cudaMemcpyAsync(d_step, h_step, sizeof(float2) * n_off, cudaMemcpyHostToDevice, st));
+        float2 *d_xy = nullptr, h_xy[64];
+        if (int rc = sc.get(&d_xy, 64)) return rc;
+        for (int o = 0; o < n_off; o++) h_xy[o] = make_float2(x_max[o], y_max);
+        PPB_CUDA(cudaMemcpyAsync(d_xy, h_xy, sizeof(float2) * n_off, cudaMemcpyHostToDevice, st));
+        PPB_CUDA(cudaStreamSynchronize(st));  // h_step / h_xy are on this frame
+        const ppb::Iter2dClass cls{reinterpret_cast<const float2 *>(d_dists), d_step, n_off, y_max, note,
+                                   make_step_search(d_xy, h_xy, n_off, 2)};
+        const int64_t n_samples = (int64_t)(0.5 * (1.0 + std::sqrt(1.0 + 8.0 * (double)n_rows)));
+        const ppb::Iter2dEmit em{n_samples, d_i, d_j, d_off};
+        ppb::bucket_count_kernel<ppb::Iter2dClass><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(cls, n_rows, n_off, hist);
+        ppb::bucket_scan_chunks_kernel<<<(unsigned)n_off, 1024, 0, st>>>(hist, blocks, n_off, tb);
+        ppb::bucket_scan_totals_kernel<<<1, ppb::kBktMax, 0, st>>>(tb, n_off, tb + ppb::kBktMax, d_count);
+        ppb::bucket_emit_kernel<ppb::Iter2dClass, ppb::Iter2dEmit><<<(unsigned)blocks, ppb::kSelThreads, 0, st>>>(
+            cls, em, n_rows, n_off, hist, tb + ppb::kBktMax, capacity);
+        g_launches += 4;
+        PPB_CUDA(cudaGetLastError());
+        return PPB_OK;
+    }
     if (int rc = sc.get(&cnt, (size_t)n_off * blocks)) return rc;
     PPB_CUDA(cudaMemcpyAsync(d_x, x_max, sizeof(float) * n_off, cudaMemcpyHostToDevice, st));
     const float2 *d2 = reinterpret_cast<const float2 *>(d_dists);
@@ -709,34 +809,112 @@ int ppb_threshold_iterate_1d_dev(const float *d_dists, int64_t n_rows, const dou
     for (int o = 0; o < n_off; o++) iterate_1d_boundary(offsets[o], slope, x0, y0, x1, y1, &bnd[o].x, &bnd[o].y);
     Scratch sc(st);
     float2 *d_bnd = nullptr;
+    unsigned long long *counters = nullptr;  // [0] non-monotone rows, [1] rows emitted, [2..3] the (key, row) where the walk stops
+    if (int rc = sc.get(&d_bnd, (size_t)n_off)) return rc;
+    if (int rc = sc.get(&counters, 4)) return rc;
+    PPB_CUDA(cudaMemcpyAsync(d_bnd, bnd.data(), sizeof(float2) * n_off, cudaMemcpyHostToDevice, st));
+    PPB_CUDA(cudaMemsetAsync(counters, 0, 32, st));
+    const float2 *d2 = reinterpret_cast<const float2 *>(d_dists);
+    int64_t *hist = nullptr, *tb = nullptr;
+    if (int rc = sc.get(&tb, 512)) return rc;
+
+    // ---- fast path: only the rows some offset admits are sorted
+    if (n_off < 65535 && !std::getenv("PPB_ITERATE1D_FULL")) {
+        uint32_t *key = nullptr, *blk_key = nullptr, *bits = nullptr, *unit_count = nullptr;
+        uint16_t *first16 = nullptr;
+        int64_t *blk_row = nullptr, *unit_off = nullptr, *m_dev = nullptr;
+        const int64_t cblocks = (n_rows + 256 * ppb::kCls1dRows - 1) / (256 * ppb::kCls1dRows);
+        const int64_t units = (n_rows + ppb::kUnitRows - 1) / ppb::kUnitRows;
+        if (int rc = sc.get(&key, (size_t)n_rows)) return rc;
+        if (int rc = sc.get(&first16, (size_t)n_rows)) return rc;
+        if (int rc = sc.get(&blk_key, (size_t)cblocks)) return rc;
+        if (int rc = sc.get(&blk_row, (size_t)cblocks)) return rc;
+        if (int rc = sc.get(&bits, (size_t)units * 32)) return rc;
+        if (int rc = sc.get(&unit_count, (size_t)units)) return rc;
+        if (int rc = sc.get(&unit_off, (size_t)units)) return rc;
+        if (int rc = sc.get(&m_dev, 1)) return rc;
+        ppb::iterate1d_classify_kernel<<<(unsigned)cblocks, 256, 0, st>>>(d2, n_rows, slope, d_bnd, n_off, key, first16, counters,
+                                                                         blk_key, blk_row,
+                                                                         make_step_search(d_bnd, bnd.data(), n_off, slope));
+        ppb::iterate1d_cut_kernel<<<1, 1024, 0, st>>>(blk_key, blk_row, cblocks, counters + 2);
+        const unsigned sgrid = (unsigned)std::min<int64_t>((units + 7) / 8, 148 * 16);
+        ppb::select_mark_kernel<ppb::PredAdmitted><<<sgrid, 256, 0, st>>>(ppb::PredAdmitted{first16, n_off}, n_rows, bits, unit_count);
+        ppb::unit_scan_kernel<<<1, 1024, 0, st>>>(unit_count, units, unit_off, m_dev);
+        g_launches += 4;
+        PPB_CUDA(cudaGetLastError());
+        unsigned long long h_irregular = 0;
+        int64_t m = 0;
+        PPB_CUDA(cudaMemcpyAsync(&h_irregular, counters, 8, cudaMemcpyDeviceToHost, st));
+        PPB_CUDA(cudaMemcpyAsync(&m, m_dev, 8, cudaMemcpyDeviceToHost, st));
+        PPB_CUDA(cudaStreamSynchronize(st));
+        if (h_irregular == 0) {
+            if (m == 0) return PPB_OK;  // (d_count is already 0)
+            uint32_t *ck = nullptr, *ck2 = nullptr;
+            int64_t *cv = nullptr, *cv2 = nullptr, *order = nullptr;
+            int32_t *first = nullptr, *block_max = nullptr;
+            const int64_t blocks = (m + ppb::kScanBlock - 1) / ppb::kScanBlock;
+            const int64_t chunks = (m + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+            if (int rc = sc.get(&ck, (size_t)m)) return rc;
+            if (int rc = sc.get(&ck2, (size_t)m)) return rc;
+            if (int rc = sc.get(&cv, (size_t)m)) return rc;
+            if (int rc = sc.get(&cv2, (size_t)m)) return rc;
+            if (int rc = sc.get(&order, (size_t)m)) return rc;
+            if (int rc = sc.get(&first, (size_t)m)) return rc;
+            if (int rc = sc.get(&block_max, (size_t)blocks)) return rc;
+            if (int rc = sc.get(&hist, (size_t)chunks * 256)) return rc;
+            ppb::select_emit_kernel<ppb::OutKeyed><<<sgrid, 256, 0, st>>>(bits, unit_count, unit_off, n_rows,
+                                                                         ppb::OutKeyed{key, first16, ck, cv}, m);
+            g_launches++;
+            uint32_t *ka = ck, *kb = ck2;
+            int64_t *va = cv, *vb = cv2;
+            for (int ps = 0; ps < 4; ps++) {  // stable: equal distances keep row order, like the reference's stable sort
+                if (int rc = radix_pass(ppb::DigitOfU32{ka, ps * 8}, ppb::MovePair{ka, va, kb, vb}, m, hist, tb, tb + 256, st)) return rc;
+                std::swap(ka, kb);
+                std::swap(va, vb);
+            }
+            ppb::iterate1d_unpack_kernel<<<(unsigned)blocks, 1024, 0, st>>>(va, m, order, first, block_max);
+            ppb::max_scan_kernel<<<1, 1024, 0, st>>>(block_max, blocks);
+            ppb::iterate1d_emit_kernel<<<(unsigned)blocks, ppb::kScanBlock, 0, st>>>(order, first, block_max, m, n_off, capacity, d_i,
+                                                                                     d_j, d_off, counters + 1, n_rows, ka, counters + 2);
+            g_launches += 3;
+            PPB_CUDA(cudaGetLastError());
+            PPB_CUDA(cudaMemcpyAsync(d_count, counters + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+            return PPB_OK;
+        }
+        PPB_CUDA(cudaMemsetAsync(counters, 0, 32, st));  // some row's test flips back with a later offset: the exact walk below
+    }
+
+    // ---- general path: every row is ranked (stable radix sort), then the walk as a running maximum — or, if a row's
+    // test is not monotone in the offset (float rounding), the reference's sequential walk verbatim
     uint32_t *k_in = nullptr, *k_out = nullptr;
     int64_t *r_in = nullptr, *order = nullptr;
     int32_t *first = nullptr, *block_max = nullptr;
-    unsigned long long *counters = nullptr;  // [0] non-monotone rows, [1] rows emitted
     const int64_t blocks = (n_rows + ppb::kScanBlock - 1) / ppb::kScanBlock;
-    if (int rc = sc.get(&d_bnd, (size_t)n_off)) return rc;
     if (int rc = sc.get(&k_in, (size_t)n_rows)) return rc;
     if (int rc = sc.get(&k_out, (size_t)n_rows)) return rc;
     if (int rc = sc.get(&r_in, (size_t)n_rows)) return rc;
     if (int rc = sc.get(&order, (size_t)n_rows)) return rc;
     if (int rc = sc.get(&first, (size_t)n_rows)) return rc;
     if (int rc = sc.get(&block_max, (size_t)blocks)) return rc;
-    if (int rc = sc.get(&counters, 2)) return rc;
-    PPB_CUDA(cudaMemcpyAsync(d_bnd, bnd.data(), sizeof(float2) * n_off, cudaMemcpyHostToDevice, st));
-    PPB_CUDA(cudaMemsetAsync(counters, 0, 16, st));
-    const float2 *d2 = reinterpret_cast<const float2 *>(d_dists);
     ppb::iterate1d_keys_kernel<<<grid_for(n_rows, 256, 148 * 16), 256, 0, st>>>(d2, n_rows, slope, bnd[0].x, bnd[0].y, k_in, r_in);
-    // stable LSD radix sort (CUB): equal distances keep row order, like the reference's stable sort
-    size_t temp_bytes = 0;
-    PPB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, k_in, k_out, r_in, order, n_rows, 0, 32, st));
-    uint8_t *temp = nullptr;
-    if (int rc = sc.get(&temp, temp_bytes)) return rc;
-    PPB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, r_in, order, n_rows, 0, 32, st));
+    {
+        const int64_t chunks = (n_rows + ppb::kSelBlockRows - 1) / ppb::kSelBlockRows;
+        if (int rc = sc.get(&hist, (size_t)chunks * 256)) return rc;
+        uint32_t *ka = k_in, *kb = k_out;
+        int64_t *va = r_in, *vb = order;
+        for (int ps = 0; ps < 4; ps++) {
+            if (int rc = radix_pass(ppb::DigitOfU32{ka, ps * 8}, ppb::MovePair{ka, va, kb, vb}, n_rows, hist, tb, tb + 256, st))
+                return rc;
+            std::swap(ka, kb);
+            std::swap(va, vb);
+        }
+        order = va;  // four passes: the sorted order is back in the first pair of buffers
+    }
     ppb::iterate1d_first_kernel<<<(unsigned)blocks, ppb::kScanBlock, 0, st>>>(d2, order, n_rows, slope, d_bnd, n_off, first,
                                                                               block_max, counters);
     ppb::max_scan_kernel<<<1, 1024, 0, st>>>(block_max, blocks);
     ppb::iterate1d_emit_kernel<<<(unsigned)blocks, ppb::kScanBlock, 0, st>>>(order, first, block_max, n_rows, n_off, capacity,
-                                                                             d_i, d_j, d_off, counters + 1);
+                                                                             d_i, d_j, d_off, counters + 1, n_rows, nullptr, nullptr);
     g_launches += 5;
     PPB_CUDA(cudaGetLastError());
     unsigned long long h[2] = {0, 0};
@@ -761,8 +939,14 @@ int ppb_knn_dev(const float *d_mat, int64_t rows, int64_t cols, int32_t knn, int
     int dev = 0, sms = 0;
     PPB_CUDA(cudaGetDevice(&dev));
     if (int rc = num_sms(dev, &sms)) return rc;
-    ppb::knn_kernel<ppb::DenseRowCands><<<(unsigned)std::min<int64_t>(rows, (int64_t)sms * 8), ppb::kKnnThreads, 0,
-                                          (cudaStream_t)stream>>>(ppb::DenseRowCands{d_mat, cols}, rows, knn, d_i, d_j, d_d);
+    if (knn <= 32 && !std::getenv("PPB_KNN_GENERIC")) {
+        ppb::knn_small_kernel<ppb::DenseRowCands><<<(unsigned)std::min<int64_t>(rows, (int64_t)sms * 8), 256, 0,
+                                                    (cudaStream_t)stream>>>(ppb::DenseRowCands{d_mat, cols, rows}, rows, knn, d_i,
+                                                                            d_j, d_d);
+    } else {
+        ppb::knn_kernel<ppb::DenseRowCands><<<(unsigned)std::min<int64_t>(rows, (int64_t)sms * 8), ppb::kKnnThreads, 0,
+                                              (cudaStream_t)stream>>>(ppb::DenseRowCands{d_mat, cols, rows}, rows, knn, d_i, d_j, d_d);
+    }
     g_launches++;
     PPB_CUDA(cudaGetLastError());
     return PPB_OK;
@@ -792,8 +976,12 @@ int ppb_extend_dev(const int64_t *d_sp_i, const int64_t *d_sp_j, const float *d_
     int dev = 0, sms = 0;
     PPB_CUDA(cudaGetDevice(&dev));
     if (int rc = num_sms(dev, &sms)) return rc;
-    ppb::knn_kernel<ppb::ExtendCands><<<(unsigned)std::min<int64_t>(n_total, (int64_t)sms * 8), ppb::kKnnThreads, 0, st>>>(
-        c, n_total, knn, d_i, d_j, d_d);
+    if (knn <= 32 && !std::getenv("PPB_KNN_GENERIC"))
+        ppb::knn_small_kernel<ppb::ExtendCands><<<(unsigned)std::min<int64_t>(n_total, (int64_t)sms * 8), 256, 0, st>>>(
+            c, n_total, knn, d_i, d_j, d_d);
+    else
+        ppb::knn_kernel<ppb::ExtendCands><<<(unsigned)std::min<int64_t>(n_total, (int64_t)sms * 8), ppb::kKnnThreads, 0, st>>>(
+            c, n_total, knn, d_i, d_j, d_d);
     g_launches += 4;
     PPB_CUDA(cudaGetLastError());
     return PPB_OK;

@@ -85,6 +85,8 @@ constexpr int kAllStages = kRings * kStages;
 constexpr int kJJUnroll = PPB_JJ_UNROLL;           // column-loop unroll inside a stage
 constexpr int kStageBytes = kJB * kSliceBytes;     // 7168
 constexpr int kCntRowWords = kTI / 2 + 4;          // 64 uint16 counts + pad: rows stay 16-B aligned (STS.128)
+constexpr int kCntRowWordsWide = kTI + 4;          // 64 uint32 counts + pad: sketches of more than 65535 bins (sketchsize64 >= 1024)
+__host__ __device__ constexpr int cnt_row_words(bool wide) { return wide ? kCntRowWordsWide : kCntRowWords; }
 constexpr int kEpiWarps = PPB_EPI_WARPS;           // epilogue warps (fit + stores): one per scheduler, so all four are loaded alike
 constexpr int kProducerWarp = kComputeWarps + kEpiWarps;  // last warp: TMA producer
 constexpr int kThreads = (kComputeWarps + 2 * 4) * 32;
@@ -114,6 +116,7 @@ struct QueryParams {
     int64_t nA, nB, nA_pad, nB_pad;
     int32_t K, n_slices, KS, G32;
     int32_t self, tj;
+    int32_t wide;         // per-k counts are uint32 in the count tile (S > 65535); the fit then computes its logs in place
     const int2 *tiles;
     int64_t n_tiles;
     int64_t row_begin, row_end;
@@ -271,7 +274,8 @@ __global__ void ytab_kernel(const QueryParams p, double *__restrict__ ytab) {
 // ------------------------------------------------------------------------------------------------
 // Per-pair epilogue: counts (shared memory) -> Jaccard -> truncated log-linear fit -> outputs.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int tj, int jl, int il) {
+__device__ __forceinline__ uint32_t read_count(const uint32_t *cnt, int t, int tj, int jl, int il, int wide) {
+    if (wide) return cnt[(t * tj + jl) * kCntRowWordsWide + il];
     const uint32_t w = cnt[(t * tj + jl) * kCntRowWords + (il >> 1)];
     return (il & 1) ? (w >> 16) : (w & 0xffffu);
 }
@@ -346,14 +350,14 @@ __device__ __forceinline__ bool pair_epilogue(const QueryParams &p, const uint32
 
     if (p.out_mode == PPB_OUT_COUNTS) {
         uint32_t *o = reinterpret_cast<uint32_t *>(p.out) + row * K;
-        for (int t = 0; t < K; t++) o[t] = read_count(cnt, t, p.tj, jl, il);
+        for (int t = 0; t < K; t++) o[t] = read_count(cnt, t, p.tj, jl, il, p.wide);
         return false;
     }
     double sy = 0.0, sxy = 0.0;
     int n = 0;
     bool open = true;
     for (int t = 0; t < K; t++) {
-        const double jac = jaccard_of_count(p, (double)read_count(cnt, t, p.tj, jl, il), rt, t);
+        const double jac = jaccard_of_count(p, (double)read_count(cnt, t, p.tj, jl, il, p.wide), rt, t);
         if (p.out_mode == PPB_OUT_JACCARD) {
             reinterpret_cast<float *>(p.out)[row * K + t] = (float)jac;
             continue;
@@ -520,26 +524,45 @@ __device__ __forceinline__ void store_counts(uint32_t dst, uint32_t r0, uint32_t
         : "memory");
 }
 
+// uint32 counts (sketches of more than 65535 bins): a slice's partial counts still fit the two 16-bit fields of a REDUX
+// word (<= 1024 per slice); they are unpacked and added to the 8 uint32 the earlier slices left (two broadcast LDS.128).
+__device__ __forceinline__ void store_counts_wide(uint32_t dst, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3,
+                                                  uint32_t lane, uint32_t accumulate, const uint4 &old_lo, const uint4 &old_hi) {
+    const uint32_t f = accumulate ? 1u : 0u;
+    uint32_t c0 = r0 & 0xffffu, c1 = r0 >> 16, c2 = r1 & 0xffffu, c3 = r1 >> 16;
+    uint32_t c4 = r2 & 0xffffu, c5 = r2 >> 16, c6 = r3 & 0xffffu, c7 = r3 >> 16;
+    c0 += old_lo.x * f, c1 += old_lo.y * f, c2 += old_lo.z * f, c3 += old_lo.w * f;
+    c4 += old_hi.x * f, c5 += old_hi.y * f, c6 += old_hi.z * f, c7 += old_hi.w * f;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %9, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t"
+        "@p st.shared.v4.u32 [%0+16], {%5,%6,%7,%8};\n\t}" ::"r"(dst),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(c5), "r"(c6), "r"(c7), "r"(lane)
+        : "memory");
+}
+
 struct SmemLayout {
     uint32_t cnt_bytes;   // one count tile
     uint32_t off_cnt, off_rinfo, off_bar, off_trash, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K, int tj) {
+__host__ __device__ inline SmemLayout smem_layout(int K, int tj, bool wide) {
     SmemLayout L;
-    L.cnt_bytes = ((uint32_t)K * tj * kCntRowWords * 4 + 127u) & ~127u;
+    L.cnt_bytes = ((uint32_t)K * tj * cnt_row_words(wide) * 4 + 127u) & ~127u;
     L.off_cnt = kAllStages * kStageBytes;
     L.off_rinfo = L.off_cnt + kCntBufs * L.cnt_bytes;
     L.off_bar = L.off_rinfo + kTI * (uint32_t)sizeof(RowInfo);
     L.off_trash = L.off_bar + (2 * kAllStages + 2 * kCntBufs) * 8;
-    L.total = L.off_trash + kComputeWarps * 16;
+    L.total = L.off_trash + kComputeWarps * 32;
     return L;
 }
 
-// kSingleSlice: S <= 1024 (one 32-group slice per k) — the common case; drops the accumulate path.
-template <bool kSingleSlice>
+// kMode 0: S <= 1024 (one 32-group slice per k) — the common case; drops the accumulate path.
+// kMode 1: several slices per k accumulate into uint16 counts.  kMode 2: ... into uint32 counts (S > 65535).
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __grid_constant__ QueryParams p) {
+    constexpr bool kSingleSlice = kMode == 0, kWide = kMode == 2;
+    constexpr int kRowW = cnt_row_words(kWide);
     extern __shared__ __align__(128) uint8_t smem[];
-    const SmemLayout L = smem_layout(p.K, p.tj);
+    const SmemLayout L = smem_layout(p.K, p.tj, kWide);
     uint8_t *stage_base = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     uint64_t *empty = full + kAllStages;
@@ -627,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
     // Software pipeline over columns: while the LOP3 stream of column c runs, the packed partial counts of
     // column c-1 go through REDUX and are stored at the end — no POPC/REDUX latency is ever waited for.
-    const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 16;
+    const uint32_t trash_addr = smem_u32(smem + L.off_trash) + warp * 32;
     const uint64_t pol_a = l2_policy(p.a_policy);  // the band's row genomes are re-read by every column tile: keep them
     uint32_t it = 0, lt = 0;
 #if PPB_STAGE_INC
@@ -651,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
         const int2 tc = p.tiles[tile];
         const int64_t i0 = (int64_t)tc.x * kTI;
         const uint32_t cb = lt % kCntBufs, cph = (lt / kCntBufs) & 1;
-        const uint32_t cnt_addr = smem_u32(smem + L.off_cnt + cb * L.cnt_bytes) + warp * (kRowsPerWarp / 2) * 4;
+        const uint32_t cnt_addr = smem_u32(smem + L.off_cnt + cb * L.cnt_bytes) + warp * (kWide ? kRowsPerWarp : kRowsPerWarp / 2) * 4;
         mbar_wait(&cempty[cb], cph ^ 1);  // the epilogue warps are done with this count tile (2 tiles ago)
 
         uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;  // packed (2 x uint16) partial counts of the previous column
@@ -686,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                     a[g][12] = v3.x, a[g][13] = v3.y;
                 }
             }
-            const uint32_t cnt_k = cnt_addr + k * tj * kCntRowWords * 4;
+            const uint32_t cnt_k = cnt_addr + k * tj * kRowW * 4;
 
             for (int jb = 0; jb < n_jb; jb++, it++) {
 #if PPB_STAGE_INC
@@ -705,11 +728,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                 mbar_wait(&full[s], ph);
                 const uint8_t *sb = stage_base + s * kStageBytes;
 #endif
-                uint32_t dst = cnt_k + jb * kJB * kCntRowWords * 4;
+                uint32_t dst = cnt_k + jb * kJB * kRowW * 4;
 #pragma unroll kJJUnroll
-                for (int jj = 0; jj < kJB; jj++, dst += kCntRowWords * 4) {
-                    uint4 old = make_uint4(0u, 0u, 0u, 0u);
+                for (int jj = 0; jj < kJB; jj++, dst += kRowW * 4) {
+                    uint4 old = make_uint4(0u, 0u, 0u, 0u), old_hi = make_uint4(0u, 0u, 0u, 0u);
                     if (!kSingleSlice) old = lds128(pdst);  // what earlier slices of this k stored for the previous column
+                    if (kWide) old_hi = lds128(pdst + 16);
 #if PPB_EARLY_PROBE
                     if (jj == kJB - 1) rready = mbar_test_addr(rbar, rph);  // next stage: usually already there
 #endif
@@ -754,7 +778,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
                         }
                         c[4] = __popc(x0), c[5] = __popc(x1), c[6] = __popc(x2), c[7] = __popc(x3);
                     }
-                    store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
+                    if (kWide)
+                        store_counts_wide(pdst, r0, r1, r2, r3, lane, pacc, old, old_hi);
+                    else
+                        store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
                     // two 16-bit partial counts per REDUX; a slice contributes <= 1024 per pair
                     pk0 = pack2(c[0], c[1]), pk1 = pack2(c[2], c[3]);
 #if PPB_DEFER_PACK
@@ -778,9 +805,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) query_kernel(const __gri
             pk2 = pack2(q4, q5), pk3 = pack2(q6, q7);
 #endif
             const uint32_t r0 = redux_add(pk0), r1 = redux_add(pk1), r2 = redux_add(pk2), r3 = redux_add(pk3);
-            uint4 old = make_uint4(0u, 0u, 0u, 0u);
+            uint4 old = make_uint4(0u, 0u, 0u, 0u), old_hi = make_uint4(0u, 0u, 0u, 0u);
             if (!kSingleSlice) old = lds128(pdst);
-            store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
+            if (kWide) {
+                old_hi = lds128(pdst + 16);
+                store_counts_wide(pdst, r0, r1, r2, r3, lane, pacc, old, old_hi);
+            } else {
+                store_counts<!kSingleSlice>(pdst, r0, r1, r2, r3, lane, pacc, old);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&cfull[cb]);  // release: this warp's counts of the tile are visible

@@ -51,6 +51,44 @@ __device__ __forceinline__ void row_to_pair(const PairMap &m, int64_t row, int64
     }
 }
 
+// ---- first admitting boundary of a row ------------------------------------------------------------------------
+// threshold_iterate_1D / 2D test a row against 20-40 boundaries that move outward (src/boundary.cpp:171-185, 211-237;
+// PopPUNK/refine.py:116-123,190-191).  In exact arithmetic a row's test flips once, from outside to inside, so the
+// first admitting boundary can be found by bisection — PROVIDED the float32 line_dist has the true sign at every
+// boundary.  That is certain wherever |line_dist| exceeds twice a bound on its rounding error taken over ALL
+// boundaries: |fl(fl(fl(y0 xm) + fl(x0 ym)) - fl(xm ym)) - exact| <= 4 u (|y0| XM + |x0| YM + XM YM), u = 2^-24
+// (slopes 0 and 1 are a single subtraction, whose sign is always exact).  A probe inside that band, a degenerate
+// boundary (an intercept of 0: the sqrt form) or boundaries that do not move outward send the row to the full scan.
+struct StepSearch {
+    const float2 *step;   // device: (x_max[o], y_max[o])
+    int32_t n_off, slope;
+    int32_t bisect;       // host-verified: intercepts positive and non-decreasing in o
+    float XM, YM;         // max |x_max|, max |y_max|
+};
+// returns the first o with line_dist_o(v) <= 0 (n_off: none), or -1 when the row needs the full scan
+__device__ __forceinline__ int32_t first_admitting_step(const StepSearch &S, const float2 v) {
+    if (!S.bisect) return -1;
+    const float guard = S.slope == 2 ? 9.6e-7f * (fabsf(v.y) * S.XM + fabsf(v.x) * S.YM + S.XM * S.YM) : 0.0f;  // 2 * 8 u * (...)
+    auto side_at = [&](int o) {
+        const float2 b = __ldg(S.step + o);
+        return line_dist(v.x, v.y, b.x, b.y, S.slope);
+    };
+    float s = side_at(S.n_off - 1);
+    if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+    if (s > 0.0f) return S.n_off;
+    s = side_at(0);
+    if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+    if (s <= 0.0f) return 0;
+    int lo = 0, hi = S.n_off - 1;  // outside at lo, inside at hi
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        s = side_at(mid);
+        if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+        if (s <= 0.0f) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
 // ---- predicates -------------------------------------------------------------------------------------------
 // A predicate is split into load(row) and test(value) so that a thread can put all its loads in flight before the
 // first ballot (a ballot is a convergence point: written as one call, every load would wait for the previous vote).

@@ -144,6 +144,150 @@ __global__ void iterate1d_keys_kernel(const float2 *__restrict__ d, int64_t n_ro
     }
 }
 
+// The fast path sorts only the rows that are EVER admitted.  iterate1d_classify_kernel makes one coalesced pass over
+// the unsorted array: key (distance to the first boundary), first admitting offset (n_off = never), the count of rows
+// whose test is not monotone in the offset, and per block the smallest (key, row) among the never-admitted rows — the
+// reference's walk stops at the first such row of the sorted order, so exactly the admitted rows that sort BEFORE that
+// (key, row) are emitted.  The admitted rows are then compacted (row order), sorted by key (stable), and walked.
+constexpr int kCls1dRows = 16;
+__global__ void __launch_bounds__(256) iterate1d_classify_kernel(const float2 *__restrict__ d, int64_t n_rows, int32_t slope,
+                                                                 const float2 *__restrict__ bnd, int32_t n_off,
+                                                                 uint32_t *__restrict__ key, uint16_t *__restrict__ first,
+                                                                 unsigned long long *__restrict__ n_irregular,
+                                                                 uint32_t *__restrict__ blk_key, int64_t *__restrict__ blk_row,
+                                                                 const StepSearch search) {
+    __shared__ uint32_t wk[8];
+    __shared__ int64_t wr[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t base = (int64_t)blockIdx.x * (256 * kCls1dRows) + (int64_t)warp * (32 * kCls1dRows);
+    float2 v[kCls1dRows];
+#pragma unroll
+    for (int m = 0; m < kCls1dRows; m++) v[m] = __ldg(d + min(base + m * 32 + lane, n_rows - 1));
+    uint32_t kmin = 0xffffffffu;
+    int64_t rmin = INT64_MAX;
+    uint32_t irregular = 0;
+#pragma unroll 2
+    for (int m = 0; m < kCls1dRows; m++) {
+        const int64_t row = base + m * 32 + lane;
+        if (row >= n_rows) continue;
+        int32_t t = first_admitting_step(search, v[m]);   // bisection where every test's sign is certain
+        bool bad = false;
+        if (t < 0) {
+            t = n_off;
+            for (int o = 0; o < n_off; o++) {
+                const float2 b = __ldg(bnd + o);
+                const bool in = line_dist(v[m].x, v[m].y, b.x, b.y, slope) <= 0.0f;
+                if (in && t == n_off) t = o;
+                if (!in && t != n_off) bad = true;
+            }
+        }
+        const float2 b0 = __ldg(bnd);
+        const uint32_t k = float_key(line_dist(v[m].x, v[m].y, b0.x, b0.y, slope));
+        key[row] = k;
+        first[row] = (uint16_t)t;
+        irregular += bad;
+        if (t == n_off && (k < kmin || (k == kmin && row < rmin))) {
+            kmin = k;
+            rmin = row;
+        }
+    }
+    irregular = __reduce_add_sync(0xffffffffu, irregular);
+    if (lane == 0 && irregular) atomicAdd(n_irregular, (unsigned long long)irregular);
+    // lexicographic minimum of (key, row): over the warp, then over the block
+    const uint32_t k_w = __reduce_min_sync(0xffffffffu, kmin);
+    const unsigned long long r_mine = kmin == k_w ? (unsigned long long)rmin : ~0ull;
+    const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(r_mine >> 32));
+    const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(r_mine >> 32) == hi ? (unsigned)r_mine : 0xffffffffu);
+    if (lane == 0) {
+        wk[warp] = k_w;
+        wr[warp] = (int64_t)(((unsigned long long)hi << 32) | lo);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bk = 0xffffffffu;
+        int64_t br = INT64_MAX;
+        for (int w = 0; w < 8; w++)
+            if (wk[w] < bk || (wk[w] == bk && wr[w] < br)) {
+                bk = wk[w];
+                br = wr[w];
+            }
+        blk_key[blockIdx.x] = bk;
+        blk_row[blockIdx.x] = br;
+    }
+}
+// (key, row) where the walk stops = the minimum over the blocks; cut[0] = key, cut[1] = row (INT64_MAX: no never-admitted row)
+__global__ void __launch_bounds__(1024) iterate1d_cut_kernel(const uint32_t *__restrict__ blk_key, const int64_t *__restrict__ blk_row,
+                                                             int64_t n_blocks, unsigned long long *__restrict__ cut) {
+    __shared__ uint32_t sk[1024];
+    __shared__ int64_t sr[1024];
+    uint32_t bk = 0xffffffffu;
+    int64_t br = INT64_MAX;
+    for (int64_t b = threadIdx.x; b < n_blocks; b += 1024) {
+        const uint32_t k = blk_key[b];
+        const int64_t r = blk_row[b];
+        if (k < bk || (k == bk && r < br)) {
+            bk = k;
+            br = r;
+        }
+    }
+    sk[threadIdx.x] = bk;
+    sr[threadIdx.x] = br;
+    __syncthreads();
+    for (int s2 = 512; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) {
+            const uint32_t k = sk[threadIdx.x + s2];
+            const int64_t r = sr[threadIdx.x + s2];
+            if (k < sk[threadIdx.x] || (k == sk[threadIdx.x] && r < sr[threadIdx.x])) {
+                sk[threadIdx.x] = k;
+                sr[threadIdx.x] = r;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cut[0] = sk[0];
+        cut[1] = (unsigned long long)sr[0];
+    }
+}
+struct PredAdmitted {  // rows some offset admits
+    typedef uint16_t Value;
+    const uint16_t *first;
+    int32_t n_off;
+    __device__ __forceinline__ uint16_t load(int64_t row) const { return __ldg(first + row); }
+    __device__ __forceinline__ bool test(const uint16_t &t) const { return (int32_t)t < n_off; }
+};
+struct OutKeyed {  // compacted (key, row | first << 48) pairs, in row order
+    const uint32_t *key;
+    const uint16_t *first;
+    uint32_t *ck;
+    int64_t *cv;
+    __device__ __forceinline__ void write(int64_t at, int64_t row) const {
+        ck[at] = key[row];
+        cv[at] = row | ((int64_t)first[row] << 48);
+    }
+};
+// sorted admitted rows -> order / first arrays + block maxima of `first` (the walk's running maximum is scanned from them)
+__global__ void __launch_bounds__(1024) iterate1d_unpack_kernel(const int64_t *__restrict__ cv, int64_t m, int64_t *__restrict__ order,
+                                                                int32_t *__restrict__ first, int32_t *__restrict__ block_max) {
+    __shared__ int32_t smax[32];
+    const int64_t p = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int32_t t = -1;
+    if (p < m) {
+        const int64_t v = cv[p];
+        t = (int32_t)(v >> 48);
+        order[p] = v & (((int64_t)1 << 48) - 1);
+        first[p] = t;
+    }
+    const int32_t wm = __reduce_max_sync(0xffffffffu, t);
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t mx = -1;
+        for (int w = 0; w < 32; w++) mx = max(mx, smax[w]);
+        block_max[blockIdx.x] = mx;
+    }
+}
+
 constexpr int kScanBlock = 1024;
 
 // first admitting offset of every sorted row (n_off = none) + block maxima + count of non-monotone rows
@@ -226,11 +370,13 @@ __global__ void __launch_bounds__(kScanBlock) iterate1d_emit_kernel(const int64_
                                                                     int32_t n_off, int64_t capacity,
                                                                     int64_t *__restrict__ out_i, int64_t *__restrict__ out_j,
                                                                     int64_t *__restrict__ out_o,
-                                                                    unsigned long long *__restrict__ n_emit) {
+                                                                    unsigned long long *__restrict__ n_emit,
+                                                                    int64_t n_rows_total, const uint32_t *__restrict__ keys,
+                                                                    const unsigned long long *__restrict__ cut) {
     __shared__ int32_t wmax[kScanBlock / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t p = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-    const int64_t n_samples = (int64_t)(0.5 * (1.0 + sqrt(1.0 + 8.0 * (double)n_rows)));
+    const int64_t n_samples = (int64_t)(0.5 * (1.0 + sqrt(1.0 + 8.0 * (double)n_rows_total)));
     int32_t x = p < n_rows ? first[p] : -1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -242,15 +388,30 @@ __global__ void __launch_bounds__(kScanBlock) iterate1d_emit_kernel(const int64_
     int32_t run = block_excl[blockIdx.x];
     for (int w = 0; w < warp; w++) run = max(run, wmax[w]);
     x = max(x, run);  // o_p
-    if (p < n_rows && x < n_off) {
-        if (p < capacity) {
-            const int64_t row = order[p];
-            const int64_t i = dev_row_idx(row, n_samples);
-            out_i[p] = i;
-            out_j[p] = dev_col_idx(row, i, n_samples);
-            out_o[p] = x;
-        }
-        atomicMax(n_emit, (unsigned long long)(p + 1));  // admitted rows are a prefix of the order
+    bool admitted = p < n_rows && x < n_off;
+    if (admitted && cut) {  // only what sorts before the first never-admitted row: that is where the reference's walk stops
+        const uint32_t ck = (uint32_t)cut[0], k = keys[p];
+        admitted = k < ck || (k == ck && order[p] < (int64_t)cut[1]);
+    }
+    if (admitted && p < capacity) {
+        const int64_t row = order[p];
+        const int64_t i = dev_row_idx(row, n_samples);
+        out_i[p] = i;
+        out_j[p] = dev_col_idx(row, i, n_samples);
+        out_o[p] = x;
+    }
+    // admitted rows are a prefix of the order: the count is the largest admitted position + 1.  One atomic per BLOCK
+    // (one per row on a single address serialised the whole kernel: 76 of its 76 ms at 400 M rows).
+    const unsigned long long mine = admitted ? (unsigned long long)(p + 1) : 0ull;
+    const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(mine >> 32));
+    const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(mine >> 32) == hi ? (unsigned)mine : 0u);
+    __shared__ unsigned long long wbest[kScanBlock / 32];
+    if (lane == 0) wbest[warp] = ((unsigned long long)hi << 32) | lo;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long best = 0;
+        for (int w = 0; w < kScanBlock / 32; w++) best = max(best, wbest[w]);
+        if (best) atomicMax(n_emit, best);
     }
 }
 
@@ -295,6 +456,7 @@ static_assert(kKnnThreads == 256, "one thread per radix bucket when the per-warp
 struct DenseRowCands {  // get_kNN_distances (extend.cpp:245-289): row r of a rows x cols matrix, j = column
     const float *mat;
     int64_t cols;
+    int64_t rows;
     __device__ __forceinline__ int64_t length(int64_t) const { return cols; }
     __device__ __forceinline__ float dist(int64_t r, int64_t pos) const { return mat[r * cols + pos]; }
     __device__ __forceinline__ int64_t j_of(int64_t, int64_t pos) const { return pos; }
@@ -327,6 +489,9 @@ struct ExtendCands {  // extend (extend.cpp:52-136): sample s < nr is a referenc
     __device__ __forceinline__ bool pad() const { return false; }
 };
 
+// (Staging each row in shared memory with one TMA bulk copy, so that the four re-reads do not go to L2, was measured
+//  and lost: 8.2 ms vs 5.5 ms at 28 k x 28 k — a 113 KB row leaves one 256-thread CTA per SM, too few warps for the
+//  shared-memory atomics of the histogram passes.  kNN <= 32 takes knn_small_kernel (one pass) instead.)
 template <typename Cands>
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_rows, int32_t knn, int64_t *__restrict__ out_i,
                                                           int64_t *__restrict__ out_j, float *__restrict__ out_d) {
@@ -338,6 +503,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
     constexpr int kBatch = 4;  // loads of a batch are issued together, before the first shared-memory atomic
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t len = c.length(r);
+        auto dist_at = [&](int64_t pos) -> float { return c.dist(r, pos); };
         // ---- (1) radix select of the knn-th smallest key among candidates with j != r
         uint32_t prefix = 0, need = (uint32_t)knn, below = 0;  // keys matching `prefix` in the decided bytes
         bool enough = true;
@@ -352,7 +518,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
                 for (int q = 0; q < kBatch; q++) {
                     const int64_t pos = p0 + (int64_t)q * kKnnThreads;
                     use[q] = pos < len && c.j_of(r, pos) != r;
-                    key[q] = float_key(c.dist(r, min(pos, len - 1)));
+                    key[q] = float_key(dist_at(min(pos, len - 1)));
                 }
 #pragma unroll
                 for (int q = 0; q < kBatch; q++)
@@ -411,7 +577,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
                 for (int q = 0; q < kBatch; q++) {
                     const int64_t pos = p0 + (int64_t)q * kKnnThreads;
                     use[q] = pos < len && c.j_of(r, pos) != r;
-                    key[q] = float_key(c.dist(r, min(pos, len - 1)));
+                    key[q] = float_key(dist_at(min(pos, len - 1)));
                 }
 #pragma unroll
                 for (int q = 0; q < kBatch; q++)
@@ -427,7 +593,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
                 bool lt = false, eq = false;
                 uint32_t key = 0;
                 if (pos < len && c.j_of(r, pos) != r) {
-                    key = float_key(c.dist(r, pos));
+                    key = float_key(dist_at(pos));
                     lt = key < prefix;
                     eq = key == prefix;
                 }
@@ -479,11 +645,81 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(Cands c, int64_t n_row
             if (t < n_sel) {
                 const int64_t pos = (int64_t)(uint32_t)sel[t];
                 j = c.j_of(r, pos);
-                dv = c.dist(r, pos);
+                dv = dist_at(pos);
             }
             out_i[o0 + t] = r;
             out_j[o0 + t] = j;
             out_d[o0 + t] = dv;
+        }
+        __syncthreads();
+    }
+}
+
+// kNN <= 32 (the lineage models' ranks: PopPUNK/models.py:1215-1222 asks for max(ranks), a handful): ONE pass over the
+// candidates.  Each of the 8 warps streams every 8th batch of the row and keeps its kNN smallest (key, position) pairs
+// sorted across its lanes; a candidate is inserted only if it beats the warp's current kNN-th (after the first few
+// batches almost none does), so the pass is a coalesced read and a compare.  The warps' lists meet in shared memory,
+// are sorted, and the first kNN are written.  (key << 32 | position) orders ties by position, as the reference does.
+template <typename Cands>
+__global__ void __launch_bounds__(256) knn_small_kernel(Cands c, int64_t n_rows, int32_t knn, int64_t *__restrict__ out_i,
+                                                        int64_t *__restrict__ out_j, float *__restrict__ out_d) {
+    __shared__ unsigned long long sel[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kU = 8;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int64_t len = c.length(r);
+        unsigned long long best = ~0ull;  // lane l: the l-th smallest pair this warp has seen
+        for (int64_t b0 = (int64_t)warp * (32 * kU); b0 < len; b0 += 8 * 32 * kU) {
+            float v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) v[u] = c.dist(r, min(b0 + u * 32 + lane, len - 1));
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int64_t pos = b0 + u * 32 + lane;
+                const bool ok = pos < len && c.j_of(r, pos) != r;
+                const unsigned long long x = ok ? (((unsigned long long)float_key(v[u]) << 32) | (unsigned long long)(uint32_t)pos) : ~0ull;
+                unsigned m = __ballot_sync(0xffffffffu, x < __shfl_sync(0xffffffffu, best, knn - 1));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long xs = __shfl_sync(0xffffffffu, x, src);
+                    if (xs < __shfl_sync(0xffffffffu, best, knn - 1)) {   // (uniform) still among the kNN smallest
+                        const int at = __ffs(__ballot_sync(0xffffffffu, best > xs)) - 1;
+                        const unsigned long long up = __shfl_up_sync(0xffffffffu, best, 1);
+                        if (lane > at) best = up;
+                        else if (lane == at) best = xs;
+                    }
+                }
+            }
+        }
+        sel[threadIdx.x] = lane < knn ? best : ~0ull;
+        __syncthreads();
+        for (uint32_t k2 = 2; k2 <= 256; k2 <<= 1)
+            for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                const uint32_t t = threadIdx.x, partner = t ^ j2;
+                if (partner > t) {
+                    const unsigned long long a = sel[t], b = sel[partner];
+                    const bool up = (t & k2) == 0;
+                    if ((a > b) == up) {
+                        sel[t] = b;
+                        sel[partner] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        const int64_t o0 = c.out_pos(r, knn);
+        if ((int)threadIdx.x < knn) {
+            const unsigned long long e = sel[threadIdx.x];
+            if (e != ~0ull) {
+                const int64_t pos = (int64_t)(uint32_t)e;
+                out_i[o0 + threadIdx.x] = r;
+                out_j[o0 + threadIdx.x] = c.j_of(r, pos);
+                out_d[o0 + threadIdx.x] = c.dist(r, pos);
+            } else if (c.pad()) {  // fewer candidates than kNN: zero padded (extend.cpp:262-274 sizes rows*kNN)
+                out_i[o0 + threadIdx.x] = r;
+                out_j[o0 + threadIdx.x] = 0;
+                out_d[o0 + threadIdx.x] = 0.0f;
+            }
         }
         __syncthreads();
     }

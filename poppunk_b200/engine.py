@@ -397,8 +397,9 @@ def query_edges(ref: PackedSketches, qry: Optional[PackedSketches], kmers, bound
             n_edges.data_ptr(), None, None, ndeg.data_ptr(), _stream_ptr(dev)), "ppb_query_edges_dev")
         n = int(n_edges.item())
         kept = edge_rows[:min(n, capacity)]
-        if sort:
-            kept = torch.sort(kept).values          # plumbing: restores the reference's row order
+        if sort:                                    # the reference's row order (the kernel appends unordered)
+            check(L.ppb_sort_rows_dev(kept.data_ptr(), kept.numel(), max(total - 1, 0), _stream_ptr(dev)),
+                  "ppb_sort_rows_dev")
         oi = torch.empty_like(kept)
         oj = torch.empty_like(kept)
         check(L.ppb_rows_to_pairs_dev(kept.data_ptr(), kept.numel(), int(self_mode), ref.n, int(int_offset),

@@ -212,3 +212,55 @@ def test_knn_zero_and_limits(eng):
     assert refine.get_kNN_distances(m, 0) == ([], [], [])
     with pytest.raises(ValueError):
         refine.get_kNN_distances(m, refine.KNN_MAX + 1)
+
+
+def test_ordered_stream_primitives_at_size(eng, oracle, monkeypatch):
+    """The hand-written ordered primitives (csrc/ppb_sort.cuh) across thousands of chunks: single-pass compaction with
+    look-back, the bucket scatter behind thresholdIterate2D (new path == generic path == oracle, with boundaries that
+    repeat and rows that sit exactly on them), the radix sort behind thresholdIterate1D and behind the fused edge list."""
+    import torch
+    from poppunk_b200 import _lib, refine
+    rng = np.random.default_rng(11)
+    n = 3000
+    rows = n * (n - 1) // 2                       # 4,498,500 rows: 1099 chunks of 4096
+    d = np.round(rng.random((rows, 2)) * 0.6, 3).astype(np.float32)
+    got = refine.edgeThreshold(d, 2, 0.21, 0.17)
+    ei, ej = oracle.edge_iterate(d, 2, 0.21, 0.17)
+    assert got == list(zip(ei.tolist(), ej.tolist())) and len(got) > 100_000
+    lab = oracle.assign_threshold(d, 2, 0.21, 0.17).astype(np.int8)
+    ti, tj = oracle.generate_tuples(lab.astype(np.int32), -1)
+    assert refine.generateTuples(lab, -1) == list(zip(ti.tolist(), tj.tolist()))
+    # 2D: steps that repeat (nothing new is admitted), a y intercept rows sit exactly on (quantised distances)
+    xm = np.array([0.0, 0.05, 0.05, 0.1, 0.2, 0.2, 0.3, 0.45, 0.6, 0.9], dtype=np.float32)
+    exp = _lists(oracle.threshold_iterate_2d(d, xm, 0.3))
+    new = refine.thresholdIterate2D(d, xm, 0.3)
+    monkeypatch.setenv("PPB_ITERATE2D_GENERIC", "1")
+    old = refine.thresholdIterate2D(d, xm, 0.3)
+    monkeypatch.delenv("PPB_ITERATE2D_GENERIC")
+    assert new == exp and old == exp and len(exp[0]) > 100_000
+    offs = np.linspace(-0.05, 0.5, 30)
+    # (short ranges leave most rows never admitted; positive offsets let slope 2 bisect over the boundaries, negative
+    #  ones force the full scan; the distances are quantised, so many rows sit exactly ON a boundary -> full scan too)
+    for slope, off_set in ((2, offs), (2, np.linspace(0.0, 0.5, 30)), (0, offs[:7]), (1, offs[3:])):
+        exp1 = _lists(oracle.threshold_iterate_1d(d, off_set, slope, 0.02, 0.03, 0.5, 0.45))
+        assert refine.thresholdIterate1D(d, off_set, slope, 0.02, 0.03, 0.5, 0.45) == exp1      # only admitted rows sorted
+        monkeypatch.setenv("PPB_ITERATE1D_FULL", "1")
+        assert refine.thresholdIterate1D(d, off_set, slope, 0.02, 0.03, 0.5, 0.45) == exp1      # every row sorted
+        monkeypatch.delenv("PPB_ITERATE1D_FULL")
+    # kNN <= 32: the one-pass kernel and the radix-select kernel agree (ties everywhere: two decimals)
+    sq = np.round(rng.random((700, 5000)), 2).astype(np.float32)
+    for k in (1, 5, 32):
+        one_pass = refine.get_kNN_distances(sq, k)
+        monkeypatch.setenv("PPB_KNN_GENERIC", "1")
+        assert refine.get_kNN_distances(sq, k) == one_pass
+        monkeypatch.delenv("PPB_KNN_GENERIC")
+    assert refine.get_kNN_distances(sq[:300], 5) == _lists(oracle.get_knn_distances(sq[:300], 5))
+    # the sort behind engine.query_edges
+    L = _lib.load()
+    vals = rng.integers(0, 5_000_000_000, size=3_000_001, dtype=np.int64)
+    t = torch.from_numpy(vals).cuda()
+    _lib.check(L.ppb_sort_rows_dev(t.data_ptr(), t.numel(), 5_000_000_000, torch.cuda.current_stream().cuda_stream))
+    assert (t.cpu().numpy() == np.sort(vals)).all()
+    small = torch.from_numpy(np.array([5, 3, 3, 0, 9], dtype=np.int64)).cuda()
+    _lib.check(L.ppb_sort_rows_dev(small.data_ptr(), 5, 9, torch.cuda.current_stream().cuda_stream))
+    assert small.cpu().tolist() == [0, 3, 3, 5, 9]

@@ -388,3 +388,26 @@ def test_host_path_many_chunks_ring_wraps(eng, oracle, monkeypatch, pinned):
         b, e = 1234, exp.shape[0] - 777                          # a shard that starts and ends inside row tiles
         part, _, _ = eng.query_host(ref, q, KMERS, row_begin=b, row_end=e)
         assert (part == got[b:e]).all()
+
+
+# ---------------------------------------------------------------- sketches of more than 65535 bins (uint32 count tile)
+@pytest.mark.parametrize("n,ss64", [(70, 1024), (5, 1500), (4, 15625)])
+def test_huge_sketches_counts_and_distances(eng, oracle, n, ss64):
+    """PopPUNK accepts --sketch-size up to 10^6 bins (__main__.py:310): sketchsize64 = 15625.  Above 1023 the per-k counts
+    no longer fit uint16; the kernel then keeps uint32 counts (and fits with in-place logs)."""
+    kmers = np.array([15, 21, 29], dtype=np.int32)
+    ref = _sk(n, ss64, kmers=kmers, n_lineages=2, chunk=8)
+    cnt, _, _ = eng.query_host(ref, None, kmers, out_mode=eng.OUT_COUNTS)
+    cnt_o, _ = oracle.query(ref, None, kmers, out_mode=oracle.OUT_COUNTS)
+    assert (cnt == cnt_o).all() and (ss64 < 1500 or int(cnt.max()) > 65535)   # the two big ones really overflow uint16
+    tab, cl = synth.random_match_table(kmers, 2), synth.synth_clusters(n, 2)
+    d, lab, ndeg = eng.query_host(ref, None, kmers, tab, cl, boundary=(2, 0.02, 0.2, 1.0, 1.0))
+    d_o, lab_o, ndeg_o = oracle.query(ref, None, kmers, tab, cl, boundary=(2, 0.02, 0.2, 1.0, 1.0))
+    assert ndeg == ndeg_o and np.abs(d - d_o).max() <= TOL
+    same = (d == d_o).all(axis=1)
+    assert (lab[same] == lab_o[same]).all()
+    if n >= 5:
+        qry = _sk(3, ss64, kmers=kmers, sample_seed=1, n_lineages=2, chunk=8)
+        dq, _, _ = eng.query_host(ref, qry, kmers)
+        dq_o, _ = oracle.query(ref, qry, kmers)
+        assert np.abs(dq - dq_o).max() <= TOL

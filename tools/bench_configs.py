@@ -49,8 +49,14 @@ def run(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # CPU-side waits while rank 0 drives all GPUs from one process
+
+    def host_barrier():
+        if host_group is not None:
+            dist.barrier(group=host_group)
 
     def barrier():
         if world > 1:
@@ -122,6 +128,7 @@ def run(args):
         del packed, out
         torch.cuda.empty_cache()
         barrier()
+        host_barrier()
         if rank == 0:
             from poppunk_b200 import sketchlib
             os.environ["PPB_DEVICES"] = str(world)
@@ -134,6 +141,7 @@ def run(args):
             e2e = {"first_call_ms": ts[0] * 1e3, "reuse_call_ms": ts[1] * 1e3, "steady_ms": min(ts[2:]) * 1e3,
                    "value": total / min(ts[2:]), "unit": "pairs/s", "h2d_bytes_per_step": int(host.nbytes),
                    "d2h_bytes_per_step": total * 8, "api": f"sketchlib.query_arrays, one process, {world} GPU(s)"}
+        host_barrier()
         barrier()
         lop3_pair = len(kmers) * ss64 * 2 * 14
         rows_rank = e - b
@@ -215,6 +223,8 @@ def run(args):
             del gathered
         else:
             q_all = qh
+        torch.cuda.synchronize()
+        host_barrier()
         if rank == 0:
             avail = _mem_available_gb()
             if avail > total / 1e9 * 1.3 + 40:
@@ -234,6 +244,7 @@ def run(args):
                               "queries scattered by the library (each device uploads only its own), labels streamed per row chunk"}
             else:
                 e2e = {"skipped": f"host has {avail:.0f} GB available; {total / 1e9:.0f} GB of labels + sketches do not fit comfortably"}
+        host_barrier()
         barrier()
         line = {"config": "cfg4", "metric": "genome-pairs/sec, query-vs-ref with fused assign_threshold",
                 "workload": f"{Q} queries x {R} refs, S=1024, K=5, random_correct on, boundary slope 2 (0.02, 0.25); "

@@ -68,19 +68,28 @@ scratch = torch.empty(L.ppb_edges_scratch_bytes(rows), dtype=torch.uint8, device
 ms = timed(lambda: _lib.check(L.ppb_edges_from_dists_dev(d.data_ptr(), rows, n_samples, 2, C.c_float(0.05), C.c_float(0.08),
                                                         oi.data_ptr(), oj.data_ptr(), rows, cnt.data_ptr(), scratch.data_ptr(), st)))
 ne = int(cnt.item())
-report(f"edge compaction: select x2 + scan ({rows} rows -> {ne} edges)", 2 * rows * 8 + ne * 16, ms, "two passes over the rows by design")
+report(f"edge compaction: single-pass select with look-back ({rows} rows -> {ne} edges)", rows * 8 + ne * 16, ms, "one read of the rows")
 xm = np.linspace(0.01, 0.3, 30).astype(np.float32)
 ms = timed(lambda: _lib.check(L.ppb_threshold_iterate_2d_dev(d.data_ptr(), rows, xm.ctypes.data, len(xm), C.c_float(0.3), oi.data_ptr(),
                                                             oj.data_ptr(), oo.data_ptr(), rows, cnt.data_ptr(), st)))
 ne = int(cnt.item())
-report(f"thresholdIterate2D: 30 steps ({rows} rows -> {ne} edges)", 2 * rows * 8 + ne * 24, ms, "two passes; 60 line_dist per row per pass")
+report(f"thresholdIterate2D: 30 steps ({rows} rows -> {ne} edges)", rows * 8 + ne * 24, ms, "one read of the rows (classify) + 1 B/row note written and read + stable scatter by step")
 offs = np.linspace(0.0, 0.3, 30)
 ms = timed(lambda: _lib.check(L.ppb_threshold_iterate_1d_dev(d.data_ptr(), rows, offs.ctypes.data, len(offs), 2, C.c_float(0.0), C.c_float(0.0),
                                                             C.c_float(0.3), C.c_float(0.3), oi.data_ptr(), oj.data_ptr(), oo.data_ptr(), rows,
                                                             cnt.data_ptr(), st)), reps=3)
 ne = int(cnt.item())
 report(f"thresholdIterate1D: 30 steps ({rows} rows -> {ne} edges)", rows * 8 + rows * 12 * 2 * 5 + ne * 24, ms,
-       "dominated by the 4-pass LSD radix sort of (key, row) pairs (CUB): ~10 x 12 B per row")
+       "dominated by the hand-written 4-pass LSD radix sort of (key, row) pairs: ~10 x 12 B per row")
+ne = min(ne, rows)
+vals = torch.randint(0, rows, (ne,), device=dev, dtype=torch.int64, generator=g)
+work = torch.empty_like(vals)
+def sort_rows():
+    work.copy_(vals)
+    _lib.check(L.ppb_sort_rows_dev(work.data_ptr(), ne, rows - 1, st))
+ms = timed(sort_rows, reps=3)
+report(f"sort_rows (radix, {ne} int64 keys < {rows}: 4 passes)", ne * 16 + ne * 8 * 3 * 4, ms, "copy + 4 x (count read, emit read + write)")
+del vals, work
 del oi, oj, oo, lab
 # long <-> square
 sq = torch.empty((n_samples, n_samples), dtype=torch.float32, device=dev)
