@@ -392,7 +392,7 @@ int host_worker(HostJob &job, int g) {
             size_t len;
             size_t piece0;       // index of its first piece
         };
-        constexpr size_t kXferBytes = (size_t)32 << 20, kPieceBytes = (size_t)4 << 20;
+        constexpr size_t kXferBytes = (size_t)16 << 20, kPieceBytes = (size_t)4 << 20;   // (pinned memory costs ~0.5 s per GiB to get)
         constexpr int kPinRing = 8;
         std::vector<Xfer> xfers;
         std::vector<size_t> chunk_x0(chunks.size() + 1, 0);  // transfers of chunk c: [chunk_x0[c], chunk_x0[c+1])
@@ -672,6 +672,17 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
     } else {
         G = (int)std::max<int64_t>(1, std::min<int64_t>(G, (row_end - row_begin) >> 24));
     }
+    // A pageable destination is drained by the host cores (first touch + copy: 30-45 GB/s on the B200 hosts measured,
+    // tools/host_floor.cu), which is less than ONE device produces at S = 1024 with 8 B per pair: more devices would only
+    // add their start-up cost (context, workspace, pinned rings: 4.5 s instead of 1.8 s for a first call with 8 devices).
+    // Use as many devices as it takes to out-produce the host, plus one.
+    const bool staged_dest = (out && !is_dma_able(out)) || (labels && !is_dma_able(labels));
+    if (staged_dest && G > 1 && !std::getenv("PPB_STAGED_ALL_DEVICES")) {
+        const double per_row = (out ? out_row_bytes(out_mode, K) : 0) + (labels ? 1 : 0);
+        const double rows_per_s = 15e12 / ((double)K * 2.0 * sketchsize64 * 14.0);   // ~0.8 of the LOP3 pipe of one B200
+        const int enough = (int)std::ceil(40e9 / (rows_per_s * per_row)) + 1;
+        G = std::max(1, std::min(G, enough));
+    }
     job.G = G;
     job.devs.assign(device_ids, device_ids + G);
     plan_device_shards(n_ref, n_qry, self, row_begin, row_end, G, &job.row_cut);
@@ -696,7 +707,7 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
     const int64_t n_pad = round_up(std::max<int64_t>(n_ref, 1), ppb::kPad);
     job.gen_cut.assign((size_t)G + 1, n_pad);
     for (int g = 0; g < G; g++) job.gen_cut[g] = std::min<int64_t>(n_pad, round_up((int64_t)((__int128)n_pad * g / G), 4));
-    job.staged = (out && !is_dma_able(out)) || (labels && !is_dma_able(labels));
+    job.staged = staged_dest;
     job.trace = std::getenv("PPB_HOST_TRACE") != nullptr;
     int hw = (int)std::thread::hardware_concurrency();
     {

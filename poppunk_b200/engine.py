@@ -298,7 +298,7 @@ def query_host(ref: np.ndarray, qry: Optional[np.ndarray], kmers, rand_table=Non
     elif out is not None and (not out.flags.c_contiguous or not out.flags.writeable):
         raise ValueError("out must be a writeable C-contiguous array")
     bnd = _boundary(boundary)
-    labels = np.empty(rows, dtype=np.int8) if bnd is not None else None
+    labels = host_result((rows,), np.int8) if bnd is not None else None   # pool block, like the distances
     ndeg = C.c_int64(0)
     devs = [int(device_id)] if devices is None else [int(d) for d in devices]
     dev_arr = (C.c_int32 * len(devs))(*devs)

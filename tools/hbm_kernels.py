@@ -68,19 +68,20 @@ scratch = torch.empty(L.ppb_edges_scratch_bytes(rows), dtype=torch.uint8, device
 ms = timed(lambda: _lib.check(L.ppb_edges_from_dists_dev(d.data_ptr(), rows, n_samples, 2, C.c_float(0.05), C.c_float(0.08),
                                                         oi.data_ptr(), oj.data_ptr(), rows, cnt.data_ptr(), scratch.data_ptr(), st)))
 ne = int(cnt.item())
-report(f"edge compaction: single-pass select with look-back ({rows} rows -> {ne} edges)", rows * 8 + ne * 16, ms, "one read of the rows")
+report(f"edge compaction: mark + scan + emit ({rows} rows -> {ne} edges)", rows * 8 + ne * 16, ms, "one read of the rows; the emit pass reads a bit per row")
 xm = np.linspace(0.01, 0.3, 30).astype(np.float32)
 ms = timed(lambda: _lib.check(L.ppb_threshold_iterate_2d_dev(d.data_ptr(), rows, xm.ctypes.data, len(xm), C.c_float(0.3), oi.data_ptr(),
                                                             oj.data_ptr(), oo.data_ptr(), rows, cnt.data_ptr(), st)))
 ne = int(cnt.item())
 report(f"thresholdIterate2D: 30 steps ({rows} rows -> {ne} edges)", rows * 8 + ne * 24, ms, "one read of the rows (classify) + 1 B/row note written and read + stable scatter by step")
-offs = np.linspace(0.0, 0.3, 30)
+offs = np.linspace(0.01, 0.3, 30)
 ms = timed(lambda: _lib.check(L.ppb_threshold_iterate_1d_dev(d.data_ptr(), rows, offs.ctypes.data, len(offs), 2, C.c_float(0.0), C.c_float(0.0),
                                                             C.c_float(0.3), C.c_float(0.3), oi.data_ptr(), oj.data_ptr(), oo.data_ptr(), rows,
                                                             cnt.data_ptr(), st)), reps=3)
 ne = int(cnt.item())
-report(f"thresholdIterate1D: 30 steps ({rows} rows -> {ne} edges)", rows * 8 + rows * 12 * 2 * 5 + ne * 24, ms,
-       "dominated by the hand-written 4-pass LSD radix sort of (key, row) pairs: ~10 x 12 B per row")
+report(f"thresholdIterate1D: 30 steps ({rows} rows -> {ne} edges)", rows * 8 + ne * 24, ms,
+       "algorithmic bytes = one read of the rows + the edges; the work in between: classify (6 B/row written), compaction of the "
+       "admitted rows, 4-pass radix sort of their (key, row) pairs, walk")
 ne = min(ne, rows)
 vals = torch.randint(0, rows, (ne,), device=dev, dtype=torch.int64, generator=g)
 work = torch.empty_like(vals)
@@ -103,6 +104,13 @@ k = 10
 ki = torch.empty(n_samples * k, dtype=torch.int64, device=dev)
 kj = torch.empty(n_samples * k, dtype=torch.int64, device=dev)
 kd = torch.empty(n_samples * k, dtype=torch.float32, device=dev)
-report(f"knn_kernel (n={n_samples}, kNN={k})", n_samples * n_samples * 4 + n_samples * k * 20,
+report(f"knn_small_kernel (n={n_samples}, kNN={k})", n_samples * n_samples * 4 + n_samples * k * 20,
+       timed(lambda: _lib.check(L.ppb_knn_dev(sq.data_ptr(), n_samples, n_samples, k, ki.data_ptr(), kj.data_ptr(), kd.data_ptr(), st))),
+       "one pass over the matrix (kNN <= 32)")
+k = 100
+ki = torch.empty(n_samples * k, dtype=torch.int64, device=dev)
+kj = torch.empty(n_samples * k, dtype=torch.int64, device=dev)
+kd = torch.empty(n_samples * k, dtype=torch.float32, device=dev)
+report(f"knn_kernel (n={n_samples}, kNN={k}: radix select)", n_samples * n_samples * 4 + n_samples * k * 20,
        timed(lambda: _lib.check(L.ppb_knn_dev(sq.data_ptr(), n_samples, n_samples, k, ki.data_ptr(), kj.data_ptr(), kd.data_ptr(), st))),
        "the matrix is read from HBM once and 4 more times from L2")
