@@ -78,7 +78,7 @@ DevWorkspace &workspace(int dev) {
 
 constexpr int kHostRing = 8;  // result buffers per device (chunks in flight between kernel and D2H)
 constexpr int kUpRing = 4;    // pinned staging buffers of a pageable upload
-constexpr size_t kUpPiece = (size_t)16 << 20;
+constexpr size_t kUpPiece = (size_t)32 << 20;
 enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
 enum { PIN_OUT0 = 0, PIN_UP0 = 16 };
 
@@ -336,7 +336,19 @@ int host_worker(HostJob &job, int g) {
         // rows of this device, in the coordinates of the launch (non-self: relative to its own query range)
         const int64_t shift = job.self ? 0 : q_lo * job.n_ref;
         std::vector<std::pair<int64_t, int64_t>> chunks;
-        plan_chunks(job.n_ref, n_q, job.self, r_lo - shift, r_hi - shift, cap, &chunks);
+        {   // ramp: the first launches are small (cap/8, cap/4, cap/2), so the first device-to-host copy starts a
+            // millisecond after the first launch instead of ten — as long as a launch still covers whole row tiles
+            int64_t r = r_lo - shift;
+            const int64_t end = r_hi - shift, tile_rows = (int64_t)ppb::kTI * job.n_ref;
+            if (!std::getenv("PPB_HOST_CHUNK_ROWS"))
+                for (int64_t c = cap / 8; c < cap && r < end && tile_rows <= c; c *= 2) {
+                    std::vector<std::pair<int64_t, int64_t>> first;
+                    plan_chunks(job.n_ref, n_q, job.self, r, std::min(end, r + c), c, &first);
+                    chunks.push_back(first.front());
+                    r = first.front().second;
+                }
+            if (r < end) plan_chunks(job.n_ref, n_q, job.self, r, end, cap, &chunks);
+        }
         int64_t max_chunk = 0;
         for (auto &c : chunks) max_chunk = std::max(max_chunk, c.second - c.first);
         int n_buf = (int)std::min<size_t>(chunks.size(), job.staged ? 4 : kHostRing);

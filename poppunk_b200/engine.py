@@ -295,8 +295,10 @@ def query_host(ref: np.ndarray, qry: Optional[np.ndarray], kmers, rand_table=Non
     if want_out and out is None:
         width, dt = (2, np.float32) if out_mode == OUT_DISTS else (K, np.float32 if out_mode == OUT_JACCARD else np.uint32)
         out = host_result((rows, width), dt)
-    elif out is not None and (not out.flags.c_contiguous or not out.flags.writeable):
-        raise ValueError("out must be a writeable C-contiguous array")
+    elif out is not None:
+        width, dt = (2, np.float32) if out_mode == OUT_DISTS else (K, np.float32 if out_mode == OUT_JACCARD else np.uint32)
+        if not out.flags.c_contiguous or not out.flags.writeable or out.dtype != dt or out.size != rows * width:
+            raise ValueError(f"out must be a writeable C-contiguous {np.dtype(dt).name} array of {rows} x {width} elements")
     bnd = _boundary(boundary)
     labels = host_result((rows,), np.int8) if bnd is not None else None   # pool block, like the distances
     ndeg = C.c_int64(0)
