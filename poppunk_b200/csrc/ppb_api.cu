@@ -347,7 +347,9 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     p.wide = wide;
 
     const size_t genome_bytes = (size_t)p.KS * ppb::kSliceBytes;
-    int band = (int)std::min<size_t>(4096, std::max<size_t>(2, kBandBytes / (genome_bytes * ppb::kTI)));
+    // at least 12 row tiles per band: at S = 16384 (143 KB per genome) the byte rule alone gives 3, and the column stream is
+    // then re-read per band — measured on a 1/8 slice of cfg5: band 3 / 6 / 12 -> 181 / 82 / 55 GB of DRAM reads, 356.7 / 354.8 / 352.7 ms
+    int band = (int)std::min<size_t>(4096, std::max<size_t>(12, kBandBytes / (genome_bytes * ppb::kTI)));
     if (const char *e = std::getenv("PPB_BAND_TILES")) band = std::max(1, atoi(e));  // tuning experiments
     // L2 eviction-priority knobs, all OFF by default: measured on B200 at N=100k (profiles/), streaming stores,
     // evict_last row-genome loads (with a persisting set-aside) and evict_first column TMA each INCREASED the

@@ -66,27 +66,35 @@ struct StepSearch {
     float XM, YM;         // max |x_max|, max |y_max|
 };
 // returns the first o with line_dist_o(v) <= 0 (n_off: none), or -1 when the row needs the full scan
-__device__ __forceinline__ int32_t first_admitting_step(const StepSearch &S, const float2 v) {
-    if (!S.bisect) return -1;
-    const float guard = S.slope == 2 ? 9.6e-7f * (fabsf(v.y) * S.XM + fabsf(v.x) * S.YM + S.XM * S.YM) : 0.0f;  // 2 * 8 u * (...)
-    auto side_at = [&](int o) {
+template <int kSlope>
+__device__ __forceinline__ int32_t bisect_steps(const StepSearch &S, const float2 v) {
+    // bisection is only allowed without degenerate boundaries, so slope 2 is line_dist's three-product form
+    // (boundary.cpp:48-50, same operations in the same order), slopes 0 / 1 one subtraction (:51-54)
+    const float guard = kSlope == 2 ? 9.6e-7f * (fabsf(v.y) * S.XM + fabsf(v.x) * S.YM + S.XM * S.YM) : -1.0f;  // 2 * 8 u * (...)
+    auto side_at = [&](int o) -> float {
         const float2 b = __ldg(S.step + o);
-        return line_dist(v.x, v.y, b.x, b.y, S.slope);
+        if (kSlope == 2) return __fsub_rn(__fadd_rn(__fmul_rn(v.y, b.x), __fmul_rn(v.x, b.y)), __fmul_rn(b.x, b.y));
+        return kSlope == 0 ? __fsub_rn(v.x, b.x) : __fsub_rn(v.y, b.y);
     };
     float s = side_at(S.n_off - 1);
-    if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+    if (!(fabsf(s) > guard)) return -1;
     if (s > 0.0f) return S.n_off;
     s = side_at(0);
-    if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+    if (!(fabsf(s) > guard)) return -1;
     if (s <= 0.0f) return 0;
     int lo = 0, hi = S.n_off - 1;  // outside at lo, inside at hi
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         s = side_at(mid);
-        if (!(fabsf(s) > guard) && S.slope == 2) return -1;
+        if (!(fabsf(s) > guard)) return -1;
         if (s <= 0.0f) hi = mid; else lo = mid;
     }
     return hi;
+}
+__device__ __noinline__ int32_t first_admitting_step(const StepSearch &S, const float2 v) {   // (one copy: callers unroll 16x)
+    if (!S.bisect) return -1;
+    if (S.slope == 2) return bisect_steps<2>(S, v);
+    return S.slope == 0 ? bisect_steps<0>(S, v) : bisect_steps<1>(S, v);
 }
 
 // ---- predicates -------------------------------------------------------------------------------------------

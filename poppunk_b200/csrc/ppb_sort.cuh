@@ -130,13 +130,30 @@ __global__ void __launch_bounds__(256) select_emit_kernel(const uint32_t *__rest
             const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        int64_t at = unit_off[u] + (incl - __popc(w));
-        const int64_t row0 = u * kUnitRows + lane * 32;
-        while (w) {
-            const int bit = __ffs(w) - 1;
-            w &= w - 1;
-            if (at < capacity) out.write(at, row0 + bit);
-            at++;
+        const uint32_t before = incl - __popc(w);                     // ... in words 0..lane-1
+        const int64_t off = unit_off[u];
+        if (unit_count[u] >= 96) {
+            // dense unit: the warp walks the non-empty words together — lane l takes row 32 m + l of word m, so the rows
+            // read and the positions written by one step are consecutive (a lane walking its own word writes 32 runs)
+            uint32_t nz = __ballot_sync(0xffffffffu, w != 0);
+            while (nz) {
+                const int m = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t wm = __shfl_sync(0xffffffffu, w, m), bm = __shfl_sync(0xffffffffu, before, m);
+                if (wm & (1u << lane)) {
+                    const int64_t at = off + bm + __popc(wm & ((1u << lane) - 1));
+                    if (at < capacity) out.write(at, u * kUnitRows + m * 32 + lane);
+                }
+            }
+        } else {
+            int64_t at = off + before;
+            const int64_t row0 = u * kUnitRows + lane * 32;
+            while (w) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                if (at < capacity) out.write(at, row0 + bit);
+                at++;
+            }
         }
     }
 }
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(kBktMax) bucket_scan_totals_kernel(const int64
 }
 
 // E: void emit(item, bucket, position)
-// Single-bucket classifiers (the radix passes) go through a staging step: every item's (bucket, item) is first put at its
+// Chunks go through a staging step: every item's (bucket, item) is first put at its
 // chunk-local sorted slot in shared memory, then consecutive threads write consecutive slots — runs of one bucket go to
 // consecutive positions, so the stores coalesce (written directly, a warp's 32 stores hit ~32 buckets: 15.7 ms per
 // pass of 400 M pairs, all of it in the store path).
@@ -249,11 +266,13 @@ template <typename C, typename E>
 __global__ void __launch_bounds__(kSelThreads) bucket_emit_kernel(C cls, E em, int64_t n, int32_t n_buckets,
                                                                   const int64_t *__restrict__ hist,
                                                                   const int64_t *__restrict__ bucket_base, int64_t capacity) {
+    constexpr uint32_t kNone16 = 0xFFFFu, kSeveral16 = 0xFFFEu;
     __shared__ uint32_t wcnt[kSelThreads / 32][kBktMax];
-    __shared__ int64_t run[kSelThreads / 32][kBktMax];
-    __shared__ uint32_t staged[kSelBlockRows];   // (bucket << 16 | item - chunk base) at its local slot
-    __shared__ uint32_t lstart[kBktMax];         // first local slot of each bucket
-    __shared__ int64_t gstart[kBktMax];          // final position of that slot
+    __shared__ uint32_t run[kSelThreads / 32][kBktMax];   // items of bucket b placed so far, counted from the chunk's first
+    __shared__ uint32_t staged[kSelBlockRows];            // (bucket << 16 | item - chunk base) at its local slot
+    __shared__ uint16_t scode[kSelBlockRows];             // every item's bucket (kNone16 / kSeveral16)
+    __shared__ uint32_t lstart[kBktMax];                  // first local slot of each bucket
+    __shared__ int64_t gstart[kBktMax];                   // final position of that slot
     __shared__ uint32_t scan_w[kSelThreads / 32];
     __shared__ uint32_t s_total;
     for (int b = threadIdx.x; b < (kSelThreads / 32) * kBktMax; b += kSelThreads) (&wcnt[0][0])[b] = 0;
@@ -261,39 +280,45 @@ __global__ void __launch_bounds__(kSelThreads) bucket_emit_kernel(C cls, E em, i
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t chunk0 = (int64_t)blockIdx.x * kSelBlockRows;
     const int64_t base = chunk0 + (int64_t)warp * (32 * kSelIters);
-    typename C::Code codes[kSelIters];
-    bool any_multi = false;
+    // the buckets go to shared memory (two bytes per item), so the placement loop below needs no unrolling — with the
+    // codes in registers the 16x unrolled body was instruction-cache bound
+    bool any_several = false;
 #pragma unroll
     for (int m = 0; m < kSelIters; m++) {
         const int64_t item = base + m * 32 + lane;
+        uint32_t code = kNone16;
         if constexpr (C::kMulti) {
             uint64_t mask = item < n ? cls.recall(item) : 0ull;
-            codes[m] = mask;
-            any_multi |= (mask & (mask - 1)) != 0;
+            const bool several = (mask & (mask - 1)) != 0;
+            any_several |= several;
+            if (mask) code = several ? kSeveral16 : (uint32_t)(__ffsll((long long)mask) - 1);
             while (mask) {
                 atomicAdd(&wcnt[warp][__ffsll((long long)mask) - 1], 1u);
                 mask &= mask - 1;
             }
         } else {
-            const uint32_t code = item < n ? cls.recall(item) : kNoBucket;
-            codes[m] = code;
-            if (code != kNoBucket) atomicAdd(&wcnt[warp][code], 1u);
+            const uint32_t c = item < n ? cls.recall(item) : kNoBucket;
+            if (c != kNoBucket) {
+                code = c;
+                atomicAdd(&wcnt[warp][c], 1u);
+            }
         }
+        scode[warp * (32 * kSelIters) + m * 32 + lane] = (uint16_t)code;
     }
     // a chunk with an item in several buckets (threshold_iterate_2D, float rounding at a boundary) is written directly
-    const bool kStaged = !__syncthreads_or(any_multi);
+    const bool kStaged = !__syncthreads_or(any_several);
     uint32_t my_total = 0;
     for (int b = threadIdx.x; b < n_buckets; b += kSelThreads) {  // where warp w's items of bucket b start
-        int64_t acc = bucket_base[b] + hist[(int64_t)blockIdx.x * n_buckets + b];
-        if (kStaged) gstart[b] = acc;
+        gstart[b] = bucket_base[b] + hist[(int64_t)blockIdx.x * n_buckets + b];
+        uint32_t acc = 0;
 #pragma unroll
         for (int w = 0; w < kSelThreads / 32; w++) {
             run[w][b] = acc;
             acc += wcnt[w][b];
-            my_total += wcnt[w][b];
         }
+        my_total = acc;
     }
-    if (kStaged) {  // exclusive scan of the chunk's bucket totals (bucket b = thread b; n_buckets <= 256 = block size)
+    {   // exclusive scan of the chunk's bucket totals (bucket b = thread b; n_buckets <= 256 = block size)
         uint32_t x = my_total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -312,7 +337,7 @@ __global__ void __launch_bounds__(kSelThreads) bucket_emit_kernel(C cls, E em, i
     auto place = [&](uint32_t code, int64_t item) {
         const uint32_t peers = __match_any_sync(0xffffffffu, code);
         const int leader = __ffs(peers) - 1;
-        long long p0 = 0;
+        uint32_t p0 = 0;
         if (lane == leader && code != kNoBucket) {
             p0 = run[warp][code];
             run[warp][code] = p0 + __popc(peers);
@@ -320,25 +345,29 @@ __global__ void __launch_bounds__(kSelThreads) bucket_emit_kernel(C cls, E em, i
         p0 = __shfl_sync(0xffffffffu, p0, leader);
         __syncwarp();
         if (code != kNoBucket) {
-            const int64_t pos = p0 + __popc(peers & ((1u << lane) - 1));
-            if (kStaged)
-                staged[lstart[code] + (uint32_t)(pos - gstart[code])] = (code << 16) | (uint32_t)(item - chunk0);
-            else if (pos < capacity)
-                em.emit(item, code, pos);
+            const uint32_t local = p0 + __popc(peers & ((1u << lane) - 1));
+            if (kStaged) {
+                staged[lstart[code] + local] = (code << 16) | (uint32_t)(item - chunk0);
+            } else {
+                const int64_t pos = gstart[code] + local;
+                if (pos < capacity) em.emit(item, code, pos);
+            }
         }
     };
-#pragma unroll
+#pragma unroll 1
     for (int m = 0; m < kSelIters; m++) {
         const int64_t item = base + m * 32 + lane;
+        const uint32_t c16 = scode[warp * (32 * kSelIters) + m * 32 + lane];
         if constexpr (C::kMulti) {
-            const uint64_t mask = codes[m];
-            if (!__any_sync(0xffffffffu, (mask & (mask - 1)) != 0)) {
-                place(mask ? (uint32_t)(__ffsll((long long)mask) - 1) : kNoBucket, item);
-            } else {  // an item in several buckets (float rounding at a boundary): bucket by bucket keeps item order exact
+            if (!__any_sync(0xffffffffu, c16 == kSeveral16)) {
+                place(c16 == kNone16 ? kNoBucket : c16, item);
+            } else {  // an item in several buckets: bucket by bucket keeps the item order exact
+                const uint64_t mask = c16 == kSeveral16 ? cls.recall(item) : (c16 == kNone16 ? 0ull : 1ull << c16);
+#pragma unroll 1
                 for (int b = 0; b < n_buckets; b++) place(((mask >> b) & 1ull) ? (uint32_t)b : kNoBucket, item);
             }
         } else {
-            place(codes[m], item);
+            place(c16 == kNone16 ? kNoBucket : c16, item);
         }
     }
     if (kStaged) {
@@ -366,7 +395,7 @@ struct Iter2dClass {
     uint8_t *note;
     StepSearch search;    // bisection over the boundaries for rows that are clear of all of them (almost all rows)
     __device__ __forceinline__ float2 load(int64_t row) const { return __ldg(d + row); }
-    __device__ __forceinline__ uint64_t steps_of(const float2 v) const {
+    __device__ __noinline__ uint64_t steps_of(const float2 v) const {   // (the rare full scan: one copy)
         uint64_t mask = 0;
         bool prev = false;
         const float xy = __fmul_rn(v.x, y_max);   // line_dist (boundary.cpp:48-50): y0*x_max + x0*y_max - x_max*y_max

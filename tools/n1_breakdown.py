@@ -19,7 +19,7 @@ for rep in range(2):
     _lib.check(L.ppb_edges_from_dists_dev(d.data_ptr(), rows, n_samples, 2, C.c_float(0.05), C.c_float(0.08), oi.data_ptr(), oj.data_ptr(), rows, cnt.data_ptr(), scratch.data_ptr(), st))
     xm = np.linspace(0.01, 0.3, 30).astype(np.float32)
     _lib.check(L.ppb_threshold_iterate_2d_dev(d.data_ptr(), rows, xm.ctypes.data, 30, C.c_float(0.3), oi.data_ptr(), oj.data_ptr(), oo.data_ptr(), rows, cnt.data_ptr(), st))
-    offs = np.linspace(0.0, 0.3, 30)
+    offs = np.linspace(0.01, 0.3, 30)
     _lib.check(L.ppb_threshold_iterate_1d_dev(d.data_ptr(), rows, offs.ctypes.data, 30, 2, C.c_float(0.0), C.c_float(0.0), C.c_float(0.3), C.c_float(0.3), oi.data_ptr(), oj.data_ptr(), oo.data_ptr(), rows, cnt.data_ptr(), st))
     torch.cuda.synchronize()
 print("done", int(cnt.item()))
