@@ -522,7 +522,9 @@ def run_gpu(args):
             t_first, res, nd_first = call()                          # first call of the process: fresh result block, staged
             chk = check_host(res, ranges, ora, ref_np, table, clusters)
             del res
-            t_reuse, res, _ = call()                                 # block comes back from the pool and is page-locked
+            t_second, res, _ = call()                                # the block comes back from the pool: touched pages, staged
+            del res
+            t_pin, res, _ = call()                                   # second reuse: the block is page-locked inside this call
             del res
             runs = []
             for _ in range(max(3, min(args.steps, 5))):
@@ -543,12 +545,14 @@ def run_gpu(args):
                    "h2d_bytes_per_step": int(ref_np.nbytes), "d2h_bytes_per_step": int(rows_bytes), "n_devices": world,
                    "api": "poppunk_b200.sketchlib.query_arrays (= pp_queryDatabase after the DB read) in ONE process on "
                           f"{world} GPU(s) via ppb_query_host_multi: pageable NumPy sketches in, the result array the drop-in "
-                          "allocates out (library pool block: page-locked from its first reuse on, so steady-state calls are "
+                          "allocates out (library pool block: page-locked from its second reuse on, so steady-state calls are "
                           "direct DMA); median of the listed runs",
                    "first_call_ms": round(t_first * 1e3, 1), "first_call_value": total / t_first,
                    "first_call_note": "first call of the process: fresh huge-page block, result staged through the pinned "
                                       "ring and copied out by the host cores (includes the one-off workspace allocations)",
-                   "reuse_call_ms": round(t_reuse * 1e3, 1),
+                   "second_call_ms": round(t_second * 1e3, 1), "second_call_value": total / t_second,
+                   "second_call_note": "the result block comes back from the pool: touched pages, still staged (no page faults)",
+                   "pinning_call_ms": round(t_pin * 1e3, 1),
                    "pageable_np_empty_ms": [round(t * 1e3, 1) for t in t_pageable],
                    "pageable_np_empty_value": total / min(t_pageable),
                    "parity_first_call": chk, "n_degenerate": int(nd), "checksum_first_1Mi_rows": last_sum}

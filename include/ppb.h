@@ -268,10 +268,11 @@ int64_t ppb_plan_device_shards(int64_t n_ref, int64_t n_qry, int32_t self, int64
 
 /* Host memory for results the LIBRARY's caller hands on as its own (the drop-in returns a NumPy array it owns):
  * ppb_host_alloc returns a block of at least `bytes` (anonymous mapping, transparent huge pages requested) from a
- * small pool; ppb_host_free hands it back.  A block that is reused has been touched and is page-locked
- * (cudaHostRegister) on that first reuse, so from the second call of a process on results are DMA-ed straight into
- * the array the caller receives.  PPB_HOST_PIN=0 disables the page-locking; PPB_HOST_POOL_MAX_GB bounds the idle
- * bytes kept (default: half of physical memory); ppb_release_workspace() drops idle blocks.                    */
+ * small pool; ppb_host_free hands it back.  A reused block has been touched (a staged copy into it no longer
+ * page-faults) and is page-locked (cudaHostRegister) on its second reuse, after which results are DMA-ed straight
+ * into the array the caller receives.  PPB_HOST_PIN_AFTER=n changes that count (0 = never page-lock);
+ * PPB_HOST_POOL_MAX_GB bounds the idle bytes kept (default: half of physical memory); ppb_release_workspace() drops
+ * idle blocks.                                                                                                   */
 void *ppb_host_alloc(size_t bytes);
 int   ppb_host_free(void *p);
 int   ppb_host_pool_stats(size_t *bytes_held, size_t *bytes_in_use, size_t *bytes_pinned);

@@ -2,6 +2,7 @@
 // tile scheduling, launches, and the host-buffer convenience path with overlapped copies.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -104,13 +105,30 @@ void plan_tiles(const TileKey &key, std::vector<int2> *v) {
     }
 }
 
+// A host-buffer call launches one kernel per row chunk: it plans the tile lists of all its chunks up front, uploads them
+// with one copy and lends them to the launches of its thread, so no launch allocates, copies or synchronises.
+struct TileLease {
+    std::map<TileKey, TileList> lists;
+};
+thread_local TileLease *g_tile_lease = nullptr;
+
 int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
-    std::lock_guard<std::mutex> lk(g_tile_mu);
-    auto it = g_tiles.find(key);
-    if (it != g_tiles.end()) {
-        *out = it->second;
-        return PPB_OK;
+    if (g_tile_lease) {
+        auto it = g_tile_lease->lists.find(key);
+        if (it != g_tile_lease->lists.end()) {
+            *out = it->second;
+            return PPB_OK;
+        }
     }
+    {
+        std::lock_guard<std::mutex> lk(g_tile_mu);
+        auto it = g_tiles.find(key);
+        if (it != g_tiles.end()) {
+            *out = it->second;
+            return PPB_OK;
+        }
+    }
+    // built outside the lock: the copy below waits for the stream, and launches on other devices must not wait with it
     std::vector<int2> v;
     plan_tiles(key, &v);
     TileList tl;
@@ -120,7 +138,14 @@ int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
         PPB_CUDA(cudaMemcpyAsync(tl.d, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
         PPB_CUDA(cudaStreamSynchronize(stream));  // v dies at scope exit
     }
-    // bounded cache (a chunked host call uses one list per row chunk: ~40 for N=100k); evict oldest first
+    std::lock_guard<std::mutex> lk(g_tile_mu);
+    auto it = g_tiles.find(key);
+    if (it != g_tiles.end()) {  // another thread planned the same launch meanwhile
+        if (tl.d) cudaFree(tl.d);
+        *out = it->second;
+        return PPB_OK;
+    }
+    // bounded cache; evict oldest first (cudaFree waits for the launches that still read the list)
     static std::vector<TileKey> order;
     if (g_tiles.size() >= 256) {
         cudaFree(g_tiles[order.front()].d);
@@ -131,6 +156,42 @@ int get_tiles(const TileKey &key, cudaStream_t stream, TileList *out) {
     order.push_back(key);
     *out = tl;
     return PPB_OK;
+}
+
+// Column-tile width and band height of a launch (per device, K and sketch size; the same for every row range).
+struct TileShape {
+    int tj = 0, band = 0, max_smem = 0;
+};
+int tile_shape(int dev, int K, int sketchsize64, TileShape *out) {
+    const bool wide = sketchsize64 > 1023;
+    // column-tile width: the widest whose uint16 count buffer fits beside the TMA ring
+    int max_smem = 0, sm_smem = 0;
+    PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    PPB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    auto smem_need = [&](int tjv) { return (size_t)ppb::smem_layout(K, tjv, wide).total; };
+    const size_t per_cta_budget = std::min<size_t>((size_t)max_smem, (size_t)sm_smem / ppb::kCtasPerSM - 1024);
+    int tj = ppb::kMaxTJ;
+    while (tj > ppb::kJB && smem_need(tj) > per_cta_budget) tj >>= 1;
+    if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
+    const size_t genome_bytes = (size_t)K * n_slices_of(sketchsize64) * ppb::kSliceBytes;
+    // at least 12 row tiles per band: at S = 16384 (143 KB per genome) the byte rule alone gives 3, and the column stream is
+    // then re-read per band — measured on a 1/8 slice of cfg5: band 3 / 6 / 12 -> 181 / 82 / 55 GB of DRAM reads, 356.7 / 354.8 / 352.7 ms
+    int band = (int)std::min<size_t>(4096, std::max<size_t>(12, kBandBytes / (genome_bytes * ppb::kTI)));
+    if (const char *e = std::getenv("PPB_BAND_TILES")) band = std::max(1, atoi(e));  // tuning experiments
+    out->tj = tj, out->band = band, out->max_smem = max_smem;
+    return PPB_OK;
+}
+TileKey make_tile_key(int dev, int64_t n_ref, int64_t n_qry, int self, int64_t row_begin, int64_t row_end,
+                      const TileShape &shape) {
+    TileKey key{dev, self ? n_ref : n_qry, n_ref, self, shape.tj, 0, 0, shape.band};
+    if (self) {
+        key.i_lo = row_idx(row_begin, n_ref);
+        key.i_hi = row_idx(row_end - 1, n_ref);
+    } else {
+        key.i_lo = row_begin / n_ref;
+        key.i_hi = (row_end - 1) / n_ref;
+    }
+    return key;
 }
 
 int num_sms(int dev, int *out) {
@@ -334,23 +395,14 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
         p.inv_n[n] = 1.0 / n;
     }
 
-    // column-tile width: the widest whose uint16 count buffer fits beside the TMA ring
-    int max_smem = 0, sm_smem = 0;
-    PPB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    PPB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    TileShape shape;
+    if (int rc = tile_shape(dev, K, sketchsize64, &shape)) return rc;
+    const int tj = shape.tj;
+    const int max_smem = shape.max_smem;
     auto smem_need = [&](int tjv) { return (size_t)ppb::smem_layout(K, tjv, wide).total; };
-    const size_t per_cta_budget = std::min<size_t>((size_t)max_smem, (size_t)sm_smem / ppb::kCtasPerSM - 1024);
-    int tj = ppb::kMaxTJ;
-    while (tj > ppb::kJB && smem_need(tj) > per_cta_budget) tj >>= 1;
-    if (smem_need(tj) > (size_t)max_smem) return fail(PPB_ERR_ARG, "ppb_query_dev: K too large for shared memory");
     p.tj = tj;
     p.wide = wide;
 
-    const size_t genome_bytes = (size_t)p.KS * ppb::kSliceBytes;
-    // at least 12 row tiles per band: at S = 16384 (143 KB per genome) the byte rule alone gives 3, and the column stream is
-    // then re-read per band — measured on a 1/8 slice of cfg5: band 3 / 6 / 12 -> 181 / 82 / 55 GB of DRAM reads, 356.7 / 354.8 / 352.7 ms
-    int band = (int)std::min<size_t>(4096, std::max<size_t>(12, kBandBytes / (genome_bytes * ppb::kTI)));
-    if (const char *e = std::getenv("PPB_BAND_TILES")) band = std::max(1, atoi(e));  // tuning experiments
     // L2 eviction-priority knobs, all OFF by default: measured on B200 at N=100k (profiles/), streaming stores,
     // evict_last row-genome loads (with a persisting set-aside) and evict_first column TMA each INCREASED the
     // DRAM read traffic (50 -> 57..208 GB) and changed the kernel time by < 2 %.  Kept as environment knobs.
@@ -360,17 +412,9 @@ static int query_dev_impl(const uint32_t *d_ref_packed, int64_t n_ref, const uin
     if (const char *e = std::getenv("PPB_STREAM_STORES")) p.stream_stores = atoi(e);
     if (const char *e = std::getenv("PPB_A_POLICY")) p.a_policy = atoi(e);
     if (const char *e = std::getenv("PPB_B_POLICY")) p.b_policy = atoi(e);
-    if (const char *e = std::getenv("PPB_STAGGER")) p.stagger_cycles = atoi(e);
     if (const char *e = std::getenv("PPB_DEBUG_SKIP_EPILOGUE")) p.debug_skip_epilogue = atoi(e);
 
-    TileKey key{dev, p.nA, p.nB, self, tj, 0, 0, band};
-    if (self) {
-        key.i_lo = row_idx(row_begin, n_ref);
-        key.i_hi = row_idx(row_end - 1, n_ref);
-    } else {
-        key.i_lo = row_begin / n_ref;
-        key.i_hi = (row_end - 1) / n_ref;
-    }
+    const TileKey key = make_tile_key(dev, n_ref, n_qry, self, row_begin, row_end, shape);
     TileList tl;
     if (int rc = get_tiles(key, st, &tl)) return rc;
     if (tl.n == 0) return PPB_OK;

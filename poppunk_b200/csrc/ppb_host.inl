@@ -79,8 +79,8 @@ DevWorkspace &workspace(int dev) {
 constexpr int kHostRing = 8;  // result buffers per device (chunks in flight between kernel and D2H)
 constexpr int kUpRing = 4;    // pinned staging buffers of a pageable upload
 constexpr size_t kUpPiece = (size_t)32 << 20;
-enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
-enum { PIN_OUT0 = 0, PIN_UP0 = 16 };
+enum { WS_REF_RAW, WS_QRY_RAW, WS_REF, WS_QRY, WS_TAB, WS_RC, WS_QC, WS_DEG, WS_YTAB, WS_TILES, WS_OUT0, WS_LAB0 = WS_OUT0 + kHostRing };
+enum { PIN_OUT0 = 0, PIN_UP0 = 16, PIN_TILES = 32 };
 
 // true when the CUDA driver can DMA straight into / out of p (pinned / registered / managed host memory)
 bool is_dma_able(const void *p) {
@@ -116,15 +116,16 @@ void advise_hugepages(void *p, size_t bytes) {
 
 // ---- host result pool -------------------------------------------------------------------------------------------
 // The drop-in allocates the (n_pairs, 2) result itself (PopPUNK owns the returned NumPy array).  Blocks come from
-// here: anonymous mappings advised MADV_HUGEPAGE; a block handed back (the array was garbage-collected) is kept, and
-// page-locked (cudaHostRegister) the first time it is REUSED, so that from the second call of a process on the result
-// is DMA-ed straight into the array the caller receives (no staging copy, no page faults).  Measured on the 16-vCPU
+// here: anonymous mappings advised MADV_HUGEPAGE; a block handed back (the array was garbage-collected) is kept — its
+// pages are touched, so a staged copy into it no longer faults — and page-locked (cudaHostRegister) on its second
+// reuse, after which the result is DMA-ed straight into the array the caller receives (no staging copy).  Measured on the 16-vCPU
 // B200 host (tools/host_floor.cu): cudaHostAlloc 2.4 GB/s, cudaHostRegister of touched huge pages 23 GB/s, staged
 // memcpy into fresh huge pages 45 GB/s, pinned D2H 54 GB/s — so a first call is fastest through the staging ring
 // and a pinned fresh allocation never pays for a single call.
 struct HostBlock {
     size_t cap = 0;
     bool in_use = false, pinned = false, touched = false;
+    int reuses = 0;
 };
 std::mutex g_pool_mu;
 std::map<void *, HostBlock> g_pool;
@@ -194,6 +195,7 @@ struct HostJob {
     int8_t *labels;
     int self, G;
     bool p2p, staged, trace;
+    std::chrono::steady_clock::time_point t0;   // start of the call (PPB_HOST_TRACE: wall-clock stamps of the phases)
     int copy_threads;
     std::vector<int> devs;
     std::vector<int64_t> row_cut;  // G+1 row boundaries: device g computes [row_cut[g], row_cut[g+1])
@@ -276,8 +278,14 @@ int host_worker(HostJob &job, int g) {
         if (int rc = ws.get(WS_DEG, 8, &d_deg)) return rc;
         return PPB_OK;
     };
+    auto stamp = [&](const char *what) {
+        if (job.trace)
+            std::fprintf(stderr, "[ppb_query_host dev %d] %s at %.1f ms of the call\n", dev, what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - job.t0).count());
+    };
     int rc = phase_a();
     if (rc) job.err[g] = g_err;
+    stamp("workspace ready");
     if (!rv.arrive(rc == PPB_OK)) return rc;
 
     // ---- phase B: upload + pack
@@ -315,6 +323,7 @@ int host_worker(HostJob &job, int g) {
     };
     rc = phase_b();
     if (rc) job.err[g] = g_err;
+    stamp("inputs uploaded, pack enqueued");
     if (!rv.arrive(rc == PPB_OK)) return rc;
 
     // ---- phase C: row chunks.  kernel(c) on s_compute overlaps D2H(c-1, c-2, ...) on s_copy.  Chunks end on
@@ -391,6 +400,43 @@ int host_worker(HostJob &job, int g) {
             explicit LeaseScope(YtabLease *l) { g_ytab_lease = l; }
             ~LeaseScope() { g_ytab_lease = nullptr; }
         } lease_scope(lease.buf ? &lease : nullptr);
+
+        // tile lists of all launches of this device: planned here, uploaded with ONE copy and lent to the launches of this
+        // thread.  (A launch that plans its own list allocates, copies from pageable memory and synchronises its stream;
+        // with 100 chunks on each of 8 devices that serialised the devices: 4.5 s instead of 1.0 s for 5e10 labels.)
+        TileLease tile_lease;
+        {
+            TileShape shape;
+            if (int rc = tile_shape(dev, K, ss64, &shape)) return rc;
+            std::vector<int2> all, v;
+            std::vector<TileKey> keys;
+            std::vector<std::pair<size_t, size_t>> span;   // (offset, count) in `all`
+            for (auto &c : chunks) {
+                keys.push_back(make_tile_key(dev, job.n_ref, n_q, job.self, c.first, c.second, shape));
+                v.clear();
+                plan_tiles(keys.back(), &v);
+                span.emplace_back(all.size(), v.size());
+                all.insert(all.end(), v.begin(), v.end());
+            }
+            void *h_tiles = nullptr, *d_tiles = nullptr;
+            if (!all.empty()) {
+                const size_t bytes = all.size() * sizeof(int2);
+                if (int rc = ws.get_pinned(PIN_TILES, bytes, &h_tiles)) return rc;
+                if (int rc = ws.get(WS_TILES, bytes, &d_tiles)) return rc;
+                std::memcpy(h_tiles, all.data(), bytes);
+                PPB_CUDA(cudaMemcpyAsync(d_tiles, h_tiles, bytes, cudaMemcpyHostToDevice, s_compute.s));
+            }
+            for (size_t c = 0; c < chunks.size(); c++) {
+                TileList tl;
+                tl.d = span[c].second ? (int2 *)d_tiles + span[c].first : nullptr;
+                tl.n = (int64_t)span[c].second;
+                tile_lease.lists[keys[c]] = tl;
+            }
+        }
+        struct TileLeaseScope {
+            explicit TileLeaseScope(TileLease *l) { g_tile_lease = l; }
+            ~TileLeaseScope() { g_tile_lease = nullptr; }
+        } tile_lease_scope(&tile_lease);
 
         // ---- staged mode (pageable destination).  A finished chunk leaves the device in TRANSFERS of <= kXferBytes:
         // D2H into a ring of pinned slots, and a pool of copy threads drains the slots into the caller's pages in
@@ -587,6 +633,7 @@ int host_worker(HostJob &job, int g) {
         return PPB_OK;
     };
     rc = phase_c();
+    stamp("row chunks done");
     if (rc) {
         job.err[g] = g_err;
         cudaStreamSynchronize(s_compute.s);  // nothing of this call may still be running on the workspace
@@ -635,6 +682,7 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
                          const uint16_t *ref_cluster, const uint16_t *qry_cluster, int64_t row_begin, int64_t row_end,
                          int32_t out_mode, void *out, const ppb_boundary *boundary, int8_t *labels,
                          int64_t *n_degenerate, const int32_t *device_ids, int32_t n_devices) {
+    const auto t_call = std::chrono::steady_clock::now();
     if (bbits != PPB_BBITS) return fail(PPB_ERR_ARG, "ppb_query_host: bbits must be 14");
     if (!ref || !kmers || K < 1 || K > PPB_MAX_K || sketchsize64 < 1 || n_ref < 0)
         return fail(PPB_ERR_ARG, "ppb_query_host: bad argument");
@@ -721,6 +769,7 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
     for (int g = 0; g < G; g++) job.gen_cut[g] = std::min<int64_t>(n_pad, round_up((int64_t)((__int128)n_pad * g / G), 4));
     job.staged = staged_dest;
     job.trace = std::getenv("PPB_HOST_TRACE") != nullptr;
+    job.t0 = t_call;
     int hw = (int)std::thread::hardware_concurrency();
     {
         cpu_set_t set;
@@ -794,8 +843,15 @@ void *ppb_host_alloc(size_t bytes) {
     if (best != g_pool.end()) {
         HostBlock &b = best->second;
         b.in_use = true;
-        const char *pin = std::getenv("PPB_HOST_PIN");  // "0": never page-lock reused blocks
-        if (!b.pinned && b.touched && !(pin && pin[0] == '0') && ppb_device_count() > 0) {
+        b.reuses++;
+        // Page-lock a block on its SECOND reuse (PPB_HOST_PIN_AFTER, 0 = never).  Registering 40 GB costs 2-8 s (more with
+        // more CUDA contexts); a first reuse is already served well by staging into the block's touched pages (no page
+        // faults: the copy threads move ~75 GB/s, above one GPU's PCIe rate), so a process that calls two or three times
+        // never pays for the registration and one that keeps calling pays once.
+        int pin_after = 2;
+        if (const char *e = std::getenv("PPB_HOST_PIN_AFTER")) pin_after = atoi(e);
+        if (const char *e = std::getenv("PPB_HOST_PIN")) if (e[0] == '0') pin_after = 0;
+        if (!b.pinned && b.touched && pin_after > 0 && b.reuses >= pin_after && ppb_device_count() > 0) {
             if (cudaHostRegister(best->first, b.cap, cudaHostRegisterPortable) == cudaSuccess)
                 b.pinned = true;
             else

@@ -60,34 +60,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 }
 
-// The same wait on a shared-memory ADDRESS the caller keeps up to date itself (no pointer arithmetic at the wait).
-__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "PPB_WAITA_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra PPB_DONEA_%=;\n\t"
-        "bra PPB_WAITA_%=;\n\t"
-        "PPB_DONEA_%=:\n\t"
-        "}" ::"r"(bar_addr),
-        "r"(parity), "r"((uint32_t)PPB_WAIT_HINT_NS)
-        : "memory");
-}
-// non-blocking: has the phase with this parity completed?
-__device__ __forceinline__ uint32_t mbar_test_addr(uint32_t bar_addr, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar_addr), "r"(parity)
-        : "memory");
-    return done;
-}
-__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
-}
-
 // Same, for warps that are NOT on the critical path (TMA producer, epilogue).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
 #if PPB_WAIT_HINT_NS > 0

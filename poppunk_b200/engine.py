@@ -214,8 +214,8 @@ def assign_threshold(dists: torch.Tensor, slope: int, x_max: float, y_max: float
 # --------------------------------------------------------------------------------------------
 def host_result(shape, dtype) -> np.ndarray:
     """A NumPy array for a result the caller will own, backed by the library's host pool (``ppb_host_alloc``):
-    huge-page backed, and page-locked from the first time a block is reused, so that repeated calls of a process
-    receive their result by direct DMA.  The block returns to the pool when the array (and every view of it) dies."""
+    huge-page backed, kept when the array dies, page-locked from its second reuse on, so that repeated calls of a
+    process receive their result by direct DMA.  The block returns to the pool when the array (and every view of it) dies."""
     import weakref
     L = _lib.load()
     dtype = np.dtype(dtype)

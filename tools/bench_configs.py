@@ -133,13 +133,14 @@ def run(args):
             from poppunk_b200 import sketchlib
             os.environ["PPB_DEVICES"] = str(world)
             ts = []
-            for _ in range(4):
+            for _ in range(5):
                 t0 = time.perf_counter()
                 res, nd = sketchlib.query_arrays(host, None, kmers, table, cl, None, device_id=local)
                 ts.append(time.perf_counter() - t0)
                 del res
-            e2e = {"first_call_ms": ts[0] * 1e3, "reuse_call_ms": ts[1] * 1e3, "steady_ms": min(ts[2:]) * 1e3,
-                   "value": total / min(ts[2:]), "unit": "pairs/s", "h2d_bytes_per_step": int(host.nbytes),
+            e2e = {"first_call_ms": ts[0] * 1e3, "second_call_ms": ts[1] * 1e3, "pinning_call_ms": ts[2] * 1e3,
+                   "steady_ms": min(ts[3:]) * 1e3,
+                   "value": total / min(ts[3:]), "unit": "pairs/s", "h2d_bytes_per_step": int(host.nbytes),
                    "d2h_bytes_per_step": total * 8, "api": f"sketchlib.query_arrays, one process, {world} GPU(s)"}
         host_barrier()
         barrier()
@@ -234,14 +235,16 @@ def run(args):
             if avail > total / 1e9 * 1.3 + 40:
                 os.environ["PPB_DEVICES"] = str(world)
                 qcl_all = synth.synth_clusters(Q, 3, seed=11)
-                ts = []
-                for _ in range(3):
+                ts, same = [], True
+                for _ in range(5):      # first (fresh block, staged) / touched block / page-locking call / steady / steady
                     t0 = time.perf_counter()
                     _, lab_h, nd = engine.query_host(rh, q_all, kmers, table, rcl, qcl_all, boundary=bnd, want_out=False,
                                                      devices=engine.visible_devices(local))
                     ts.append(time.perf_counter() - t0)
-                same = bool((lab_h[:20_000] == lab[:20_000]).all())
+                    same = same and bool((lab_h[:20_000] == lab[:20_000]).all())
+                    del lab_h           # the block goes back to the pool before the next call asks for one
                 e2e = {"calls_ms": [round(t * 1e3, 1) for t in ts], "value": total / min(ts), "unit": "pairs/s",
+                       "calls": "first (fresh pool block, staged) / touched block, staged / page-locking call / steady / steady",
                        "h2d_bytes_per_step": int(rh.nbytes + q_all.nbytes), "d2h_bytes_per_step": total,
                        "labels_identical_to_device_run_first_20k": same,
                        "api": f"engine.query_host(..., boundary, want_out=False) = ppb_query_host_multi, one process, {world} GPU(s): "

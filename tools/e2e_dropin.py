@@ -3,7 +3,8 @@
 are in memory) on 1..all GPUs of the box, with the destinations a PopPUNK process can end up with:
     python tools/e2e_dropin.py [N=100000] [device counts, e.g. 1,2,8]
   cold      first call of the process: result block fresh from the library pool (huge pages, staged through the ring)
-  reuse     the block comes back from the pool and is page-locked on the way (registration inside the timed call)
+  second    the block comes back from the pool: touched pages, still staged
+  third     the block is page-locked on its second reuse (registration inside the timed call)
   warm      pool block already page-locked: direct DMA into the array the caller receives
   np.empty  a caller-provided fresh pageable array per call
 One JSON line per measurement."""
@@ -44,7 +45,9 @@ for g in sorted(set(c for c in counts if 1 <= c <= L.ppb_device_count())):
     L.ppb_release_workspace()
     r = run("cold (first call: fresh pool block, staged)", g)
     del r
-    r = run("reuse (pool block page-locked inside this call)", g)
+    r = run("second call (pool block reused: touched pages, staged)", g)
+    del r
+    r = run("third call (pool block page-locked inside this call)", g)
     del r
     for _ in range(3):
         r = run("warm (page-locked pool block, direct DMA)", g)
