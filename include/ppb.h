@@ -251,7 +251,7 @@ int ppb_query_host(const uint64_t *ref, int64_t n_ref,
  * chunks and copies them back straight into the ONE caller buffer.  No exchange between devices.  A job with fewer
  * than ~16 Mi rows per device uses fewer devices, and so does a PAGEABLE destination (it is drained by the host cores,
  * which one or two devices already out-produce; PPB_STAGED_ALL_DEVICES=1 overrides).  Page-locked destinations
- * (cudaHostAlloc / cudaHostRegister / ppb_host_alloc blocks after their first reuse) are written by direct DMA.
+ * (cudaHostAlloc / cudaHostRegister / ppb_host_alloc blocks after their second reuse) are written by direct DMA.
  * ppb_query_host(…, device_id) is this call with one device.                                                     */
 int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref,
                          const uint64_t *qry, int64_t n_qry,

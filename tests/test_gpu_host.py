@@ -97,6 +97,23 @@ def test_multi_device_call_matches_single(eng, oracle, monkeypatch, n_qry, p2p):
     assert (cnt == cnt_o).all()
 
 
+def test_more_launches_than_the_tile_list_cache_holds(eng, monkeypatch):
+    """A call of several hundred row chunks (cfg4 through one process has 100 per device, 800 per call on 8 GPUs): the
+    tile lists of all chunks are planned and uploaded once per call and lent to its launches.  Byte-identical to the
+    un-chunked call, call after call, staged and direct, on every device of the box."""
+    import torch
+    ref, _, tab, rcl, _ = _job(1200)
+    bnd = (2, 0.02, 0.2, 1.0, 1.0)
+    one, lab1, nd1 = eng.query_host(ref, None, KMERS, tab, rcl, boundary=bnd)
+    monkeypatch.setenv("PPB_HOST_CHUNK_ROWS", "2048")          # 352 launches: more than the 256 lists the cache keeps
+    monkeypatch.setenv("PPB_MIN_ROWS_PER_DEVICE", "1000")
+    devs = list(range(_n_dev()))
+    for _ in range(2):
+        for out in (np.full(one.shape, -1, dtype=np.float32), torch.full(one.shape, -1.0).pin_memory().numpy()):
+            got, lab, nd = eng.query_host(ref, None, KMERS, tab, rcl, boundary=bnd, out=out, devices=devs)
+            assert nd == nd1 and (got.view(np.uint32) == one.view(np.uint32)).all() and (lab == lab1).all()
+
+
 def test_host_pool_block_is_pinned_on_second_reuse(eng, oracle):
     from poppunk_b200 import _lib
     L = _lib.load()

@@ -29,4 +29,6 @@
 #   $TR --master-port 29551 bench.py --gpus 8 --steps 3
 #   $TR --master-port 29561 bench.py --gpus 8 --config cfg5 --steps 2
 #   $TR --master-port 29562 bench.py --gpus 8 --config cfg4 --steps 2
+#   PPB_HOST_PIN_AFTER=1 PPB_HOST_TRACE=1 python tools/e2e_labels.py 125000 50000 8 4 1000000      # streamed labels, one process
+#   (1 / 2 GPUs: PPB_HOST_TRACE=1 python tools/e2e_labels.py 125000 50000 1|2 ; PPB_HOST_CHUNK_ROWS=8000000 for ~1000 chunks per device)
 echo "see the comments in this file; each line is run under gpurun"
