@@ -33,8 +33,10 @@ import argparse
 import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -238,6 +240,77 @@ def recorded_traffic(n):
         return None, f"capture {t.get('source')} is of another kernel build / workload"
     except Exception:
         return None, "no capture"
+
+
+_UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def parse_ncu_dram_bytes(text):
+    """(read bytes, write bytes) of the first profiled launch in an `ncu --csv --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum` log; None when the log holds no such rows."""
+    import csv
+    import io
+    lines = [ln for ln in text.splitlines() if ln.startswith('"')]
+    got = {}
+    for row in csv.DictReader(io.StringIO("\n".join(lines))):
+        name = row.get("Metric Name")
+        if name in ("dram__bytes_read.sum", "dram__bytes_write.sum") and name not in got:
+            got[name] = float(row["Metric Value"].replace(",", "")) * _UNIT_SCALE.get(row.get("Metric Unit", "byte"), 1)
+    if len(got) != 2:
+        return None
+    return got["dram__bytes_read.sum"], got["dram__bytes_write.sum"]
+
+
+def capture_traffic(n, timeout_s=240):
+    """DRAM bytes of ONE query_kernel launch, measured in THIS run: a child process repeats the step's kernel on the same
+    inputs under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (one replay pass of the second launch).
+    Only the byte counters are taken from the profiled child — every time in the bench line is measured outside it.
+    Returns (bytes or None, source text)."""
+    if os.environ.get("PPB_BENCH_NO_NCU"):
+        return None, "in-run capture disabled (PPB_BENCH_NO_NCU)"
+    if any(k.startswith("NV_COMPUTE_PROFILER") or k == "CUDA_INJECTION64_PATH" for k in os.environ):
+        return None, "bench.py itself runs under a profiler: no nested capture"
+    ncu = os.environ.get("PPB_NCU") or shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            logf = os.path.join(td, "traffic.csv")
+            cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+                   "--print-units", "base", "-k", "regex:query_kernel", "-s", "1", "-c", "1", "--csv", "--log-file", logf,
+                   sys.executable, os.path.abspath(__file__), "--traffic-child", "--genomes", str(n)]
+            env = {k: v for k, v in os.environ.items()
+                   if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+            text = open(logf).read() if os.path.exists(logf) else ""
+        rw = parse_ncu_dram_bytes(text)
+        if rw is None:
+            tail = (text + res.stderr).strip().splitlines()[-1:] or ["no output"]
+            return None, f"in-run ncu capture gave no counters (rc={res.returncode}: {tail[0][:160]})"
+        return int(rw[0] + rw[1]), (f"in-run ncu capture (dram__bytes_read.sum {rw[0] / 1e9:.1f} GB + dram__bytes_write.sum "
+                                    f"{rw[1] / 1e9:.1f} GB of ONE launch of the same step, repeated in a child process "
+                                    "under ncu --metrics, one replay pass)")
+    except subprocess.TimeoutExpired:
+        return None, f"in-run ncu capture timed out after {timeout_s} s"
+    except Exception as ex_:   # the bench line must not depend on the profiler
+        return None, f"in-run ncu capture failed: {ex_!r}"
+
+
+def run_traffic_child(args):
+    """What capture_traffic() profiles: the timed step's inputs and two launches of its kernel (the second is captured)."""
+    import torch
+    from poppunk_b200 import engine, synth
+    n = args.n
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    sk = synth.synth_sketches_torch(n, KMERS, SS64, seed=SEED, device=dev, **POP)
+    table, clusters = workload_tables(n)
+    table_dev = torch.as_tensor(table).to(dev)
+    packed = engine.pack(sk, clusters=engine.DeviceClusters.upload(clusters, dev))
+    out = torch.empty((n * (n - 1) // 2, 2), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        engine.query(packed, None, KMERS, rand_table=table_dev, out=out)
+    torch.cuda.synchronize()
 
 
 def sample_ranges(total, world, per_rank=100_000):
@@ -604,7 +677,14 @@ def run_gpu(args):
     peaks = measured_peaks()
     peak = peaks["hbm_gbs"] if peaks else 6650.0
     ach = algorithmic_bytes(n, rows_rank) / (k_ms * 1e-3) / 1e9
-    traffic, traffic_src = recorded_traffic(n) if world == 1 else (None, "single-GPU capture only")
+    traffic, traffic_src = (None, "single-GPU capture only")
+    if world == 1:
+        torch.cuda.empty_cache()
+        traffic, traffic_src = capture_traffic(n)
+        log(f"[bench] DRAM traffic of one launch: {traffic} ({traffic_src})")
+        if traffic is None:   # fall back to the committed capture, if it is of this kernel source and workload
+            rec, rec_src = recorded_traffic(n)
+            traffic, traffic_src = rec, f"{rec_src}; {traffic_src}"
     roofline = {"bound": "hbm", "kernel": "query_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured" if peaks else "fallback",
@@ -673,8 +753,11 @@ def main():
     ap.add_argument("--config", default="north_star", choices=["north_star", "cfg2", "cfg4", "cfg5"],
                     help="north_star = the driver's bench line; cfg2/cfg4/cfg5 = the other BASELINE.json configs "
                          "(profiles/ lines, see tools/bench_configs.py)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)   # what capture_traffic() profiles
     args = ap.parse_args()
-    if args.config != "north_star":
+    if args.traffic_child:
+        run_traffic_child(args)
+    elif args.config != "north_star":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs
         bench_configs.run(args)

@@ -246,6 +246,46 @@ def test_reference_arm_under_torchrun_uses_all_cores():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 
+def test_bench_traffic_capture_plumbing(tmp_path, monkeypatch):
+    """bench.py's in-run DRAM-traffic capture: the command it hands to ncu, the CSV it reads back, and that a missing or
+    failing profiler yields (None, reason) instead of an exception — with a stand-in for the ncu binary (no GPU here)."""
+    import stat
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    fake = tmp_path / "ncu"
+    fake.write_text("""#!/bin/bash
+# stand-in: records its arguments, writes the log an ncu --csv --metrics run writes
+echo "$@" > "$(dirname "$0")/args.txt"
+while [ $# -gt 0 ]; do if [ "$1" = "--log-file" ]; then log="$2"; fi; shift; done
+cat > "$log" <<'EOF'
+==PROF== Connected to process 468 (/usr/bin/python3.12)
+"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"
+"0","468","python3.12","127.0.0.1","void query_kernel<0>(QueryParams)","1","7","(512, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","dram__bytes_read.sum","byte","202673757952"
+"0","468","python3.12","127.0.0.1","void query_kernel<0>(QueryParams)","1","7","(512, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","dram__bytes_write.sum","Gbyte","40.5"
+EOF
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    for k in list(os.environ):
+        if k.startswith("NV_COMPUTE_PROFILER") or k in ("CUDA_INJECTION64_PATH", "PPB_BENCH_NO_NCU"):
+            monkeypatch.delenv(k)
+    monkeypatch.setenv("PPB_NCU", str(fake))
+    got, src = bench.capture_traffic(100_000, timeout_s=30)
+    assert got == 202673757952 + 40_500_000_000 and "in-run ncu capture" in src
+    argv = (tmp_path / "args.txt").read_text().split()
+    assert "--traffic-child" in argv and argv[argv.index("--genomes") + 1] == "100000"
+    assert "regex:query_kernel" in argv and argv[argv.index("-s") + 1] == "1" and argv[argv.index("-c") + 1] == "1"
+    assert argv[argv.index("--metrics") + 1] == "dram__bytes_read.sum,dram__bytes_write.sum"
+    fake.write_text("#!/bin/bash\necho 'no counters for you' >&2\nexit 1\n")
+    got, src = bench.capture_traffic(100_000, timeout_s=30)
+    assert got is None and "rc=1" in src
+    monkeypatch.setenv("PPB_NCU", str(tmp_path / "absent"))
+    assert bench.capture_traffic(100_000)[0] is None
+    monkeypatch.setenv("PPB_BENCH_NO_NCU", "1")
+    assert bench.capture_traffic(100_000) == (None, "in-run capture disabled (PPB_BENCH_NO_NCU)")
+
+
 @pytest.mark.parametrize("n_ref,n_qry,self_mode,tile_cols,band", [(300, 0, True, 128, 2), (130, 0, True, 128, 64),
                                                                   (200, 0, True, 32, 3), (257, 150, False, 128, 2),
                                                                   (65, 1, False, 64, 1), (2, 0, True, 128, 4)])
