@@ -1156,9 +1156,9 @@ int64_t ppb_plan_tiles(int64_t n_ref, int64_t n_qry, int32_t self, int64_t row_b
     if (n_ref < 1 || (!self && n_qry < 1) || row_begin < 0 || row_end > total_rows || row_begin >= row_end || tile_cols < 1 ||
         band_tiles < 1)
         return -1;
-    TileKey key{0, self ? n_ref : n_qry, n_ref, self, tile_cols, 0, 0, band_tiles};
-    key.i_lo = self ? row_idx(row_begin, n_ref) : row_begin / n_ref;   // the same row-genome range ppb_query_dev derives
-    key.i_hi = self ? row_idx(row_end - 1, n_ref) : (row_end - 1) / n_ref;
+    TileShape shape;
+    shape.tj = tile_cols, shape.band = band_tiles;
+    const TileKey key = make_tile_key(0, n_ref, n_qry, self, row_begin, row_end, shape);   // as ppb_query_dev and the host call do
     std::vector<int2> v;
     plan_tiles(key, &v);
     for (size_t t = 0; t < v.size() && (int64_t)t < max_tiles && tiles; t++) {

@@ -321,6 +321,48 @@ def test_tile_schedule_covers_every_pair_once(lib, n_ref, n_qry, self_mode, tile
     assert lib.ppb_plan_tiles(n_ref, n_qry, int(self_mode), 0, total + 1, tile_cols, band, None, 0) == -1
 
 
+@pytest.mark.parametrize("n_ref,n_qry,self_mode,G,cap", [(700, 0, True, 3, 5000), (257, 150, False, 2, 3000),
+                                                        (1200, 0, True, 1, 2048), (50, 1000, False, 8, 1024)])
+def test_shards_chunks_tiles_compose(lib, n_ref, n_qry, self_mode, G, cap):
+    """The three plans a host call stacks — device shards, row chunks of a shard (in the device's own coordinates:
+    non-self shards are re-based on the first query the device holds, ppb_host.inl), tile list of a chunk — put every row
+    of the job into exactly one launch whose tile list holds the row's tile."""
+    import ctypes as C
+    total = lib.ppb_num_rows(n_ref, n_qry, int(self_mode))
+    cuts = (C.c_int64 * (G + 1))()
+    assert lib.ppb_plan_device_shards(n_ref, n_qry, int(self_mode), 0, total, G, cuts) == G
+    covered = 0
+    for g in range(G):
+        r_lo, r_hi = cuts[g], cuts[g + 1]
+        if r_hi <= r_lo:
+            continue
+        q_lo = 0 if self_mode else r_lo // n_ref
+        n_q = 0 if self_mode else (r_hi - 1) // n_ref + 1 - q_lo
+        shift = q_lo * n_ref
+        n = lib.ppb_plan_host_chunks(n_ref, n_q, int(self_mode), r_lo - shift, r_hi - shift, cap, None, 0)
+        bounds = np.zeros((n, 2), dtype=np.int64)
+        assert lib.ppb_plan_host_chunks(n_ref, n_q, int(self_mode), r_lo - shift, r_hi - shift, cap, bounds.ctypes.data, n) == n
+        assert bounds[0, 0] == r_lo - shift and bounds[-1, 1] == r_hi - shift and (bounds[1:, 0] == bounds[:-1, 1]).all()
+        for c0, c1 in bounds:
+            c0, c1 = int(c0), int(c1)
+            assert 0 < c1 - c0 <= max(cap, 64 * n_ref)
+            nt = lib.ppb_plan_tiles(n_ref, n_q, int(self_mode), c0, c1, 128, 12, None, 0)
+            tiles = np.zeros((nt, 2), dtype=np.int32)
+            assert lib.ppb_plan_tiles(n_ref, n_q, int(self_mode), c0, c1, 128, 12, tiles.ctypes.data, nt) == nt
+            listed = {(int(t), int(c)) for t, c in tiles}
+            assert len(listed) == nt
+            for r in np.unique(np.concatenate([np.arange(c0, c1, max(1, (c1 - c0) // 50)), [c1 - 1]])):
+                if self_mode:
+                    i = lib.ppb_calc_row_idx(int(r), n_ref)
+                    j = lib.ppb_calc_col_idx(int(r), i, n_ref)
+                else:
+                    i, j = int(r) // n_ref, int(r) % n_ref              # i: query index local to the device
+                    assert 0 <= i < n_q
+                assert (i // 64, j // 128) in listed, (g, c0, c1, r, i, j)
+            covered += c1 - c0
+    assert covered == total
+
+
 def test_device_shards_are_balanced_tile_aligned_and_cover(lib):
     """ppb_plan_device_shards: what ppb_query_host_multi gives each device."""
     import ctypes as C
