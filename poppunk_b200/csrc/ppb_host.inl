@@ -91,6 +91,14 @@ bool is_dma_able(const void *p) {
     }
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice;
+}
 // memcpy split over a few threads: one core cannot move 50 GB/s between a staging buffer and fresh pages
 void parallel_memcpy(void *dst, const void *src, size_t bytes, int threads) {
     if (threads <= 1 || bytes < ((size_t)4 << 20)) {
@@ -714,6 +722,11 @@ int ppb_query_host_multi(const uint64_t *ref, int64_t n_ref, const uint64_t *qry
             if (device_ids[h] == device_ids[g]) return fail(PPB_ERR_ARG, "ppb_query_host: a device is listed twice");
     }
     DeviceGuard guard;
+    // this entry reads and writes HOST memory (its copy threads memcpy into the destination); device-resident data
+    // goes through ppb_query_dev
+    for (const void *p : {(const void *)ref, (const void *)qry, (const void *)out, (const void *)labels})
+        if (is_device_ptr(p))
+            return fail(PPB_ERR_ARG, "ppb_query_host: a device pointer was passed where host memory is expected (use ppb_query_dev)");
     // one host-buffer call at a time per process (the reference's entry is not re-entrant either); two overlapping
     // multi-device calls could otherwise each hold one device's workspace and wait for the other's
     static std::mutex host_call_mu;
