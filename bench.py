@@ -25,7 +25,10 @@ Prints ONE JSON line (rank 0).
   parity    rows sampled from EVERY rank's slice of the timed result, against the CPU oracle and against a single-GPU
             recompute; the bench exits non-zero on a mismatch
   cpu_baseline  the CPU oracle (a restatement of the pp-sketchlib CPU path; the library itself is absent) on all host
-            cores, on a bounded row range of the same workload
+            cores, on a bounded row range of the same workload; "tuned" inside it = the same arithmetic re-written for
+            the host's AVX-512 (oracle/ppb_oracle_tuned.inc, bit-identical results): what the CPU can do
+  roofline.traffic  DRAM bytes of one launch, measured in this run by repeating the launch in a child process under
+            `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (only the counters come from the profiled child)
 """
 from __future__ import annotations
 
@@ -176,6 +179,36 @@ def cpu_rate(oracle, native, ref_host, table, clusters, target_s, reps=1):
     return rows / dt, threads, rows, dt
 
 
+def cpu_rate_tuned(oracle, ref_host, table, clusters, target_s):
+    """The tuned CPU arm (oracle/ppb_oracle_tuned.inc: AVX-512, cache-blocked, ln J table; bit-identical to the port) on
+    rows [0, R) of the self job.  None where the host has no AVX-512 VPOPCNTDQ."""
+    try:
+        if not oracle.tuned_available():
+            return None
+        n = ref_host.shape[0]
+        total = n * (n - 1) // 2
+        threads = host_threads()
+        probe = min(total, 2_000_000 * threads)
+        t0 = time.perf_counter()
+        got, _ = oracle.query_tuned(ref_host, KMERS, table, clusters, row_end=probe, threads=threads)
+        rate = probe / (time.perf_counter() - t0)
+        check = min(probe, 200_000)
+        exp, _ = oracle.query(ref_host, None, KMERS, table, clusters, row_begin=0, row_end=check, threads=threads, native=True)
+        same = bool((exp.view(np.uint32) == got[:check].view(np.uint32)).all())
+        rows = int(min(total, max(probe, rate * target_s)))
+        t0 = time.perf_counter()
+        oracle.query_tuned(ref_host, KMERS, table, clusters, row_end=rows, threads=threads)
+        dt = time.perf_counter() - t0
+        return {"value": rows / dt, "unit": UNIT, "cores": threads, "kind": "port, tuned",
+                "sample": f"rows [0,{rows}) of the same job ({rows} pairs), incl. its one-off repack of the sketches",
+                "identical_to_port": same,
+                "note": "same arithmetic written for the host's AVX-512 (VPTERNLOGQ 0x90 + VPOPCNTQ on plane-major sketches, "
+                        "64 x 8 genome tiles, ln J from a table): what the CPU can do, beside the upstream-shaped loop above"}
+    except Exception as ex_:
+        log(f"[bench] tuned cpu arm failed: {ex_!r}")
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (pp-sketchlib itself is
     not in /root/reference and not installable here), all host threads, bounded sample per step."""
@@ -200,6 +233,7 @@ def run_reference(args):
     value, threads, rows, dt = cpu_rate(oracle, native, ref_host, table, clusters, 8.0, reps=args.steps)
     total = n_eff * (n_eff - 1) // 2
     sample = f"rows [0,{rows}) of the N={n_eff} self job per step ({rows} pairs)"
+    tuned = cpu_rate_tuned(oracle, ref_host, table, clusters, 6.0)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -208,7 +242,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the pp-sketchlib path (oracle/ppb_oracle.c, OpenMP, "
                                  + ("-march=native" if native else "-march=x86-64-v3") + "); pp-sketchlib absent; "
-                                 "parity unpinned"},
+                                 "parity unpinned",
+                         "tuned": tuned},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -704,6 +739,7 @@ def run_gpu(args):
                    "note": "CPU restatement of the pp-sketchlib path (oracle/ppb_oracle.c, OpenMP, "
                            + ("-march=native" if native else "-march=x86-64-v3") + "); pp-sketchlib itself is absent; "
                            "parity unpinned"}
+            cpu["tuned"] = cpu_rate_tuned(oracle, ref_np, table, clusters, 6.0)
         except Exception as ex_:
             log(f"[bench] cpu baseline failed: {ex_!r}")
 

@@ -29,23 +29,53 @@ class Boundary(C.Structure):
                 ("scale_x", C.c_float), ("scale_y", C.c_float)]
 
 
+def _cpu_key() -> str:
+    """What -march=native resolved to on the machine that built libppo_native.so: the CPU's feature flags."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(" ".join(sorted(flags.split(":")[-1].split())).encode()).hexdigest()[:12]
+
+
 def build(native: bool = False) -> str:
-    """Compile the C oracle (``make -C oracle``); returns the path of the shared object."""
-    target = ["native"] if native else []
-    subprocess.run(["make", "-s", "-C", _HERE] + target, check=True)
-    return os.path.join(_HERE, "libppo_native.so" if native else "libppo.so")
+    """Compile the C oracle (``make -C oracle``); returns the path of the shared object.  The -march=native build is
+    tied to the CPU it was made on (it travels to other boxes with the tree): a sidecar file records the CPU's feature
+    flags and a different CPU forces a rebuild instead of risking an illegal instruction."""
+    if not native:
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
+        return os.path.join(_HERE, "libppo.so")
+    side = os.path.join(_HERE, "libppo_native.cpu")
+    key = _cpu_key()
+    try:
+        stale = open(side).read().strip() != key
+    except OSError:
+        stale = True
+    subprocess.run(["make", "-s", "-C", _HERE] + (["-B"] if stale else []) + ["native"], check=True)
+    with open(side, "w") as f:
+        f.write(key + "\n")
+    return os.path.join(_HERE, "libppo_native.so")
 
 
 _lib = None
+_lib_native = None
 
 
 def lib(native: bool = False):
-    global _lib
+    global _lib, _lib_native
     if _lib is not None and not native:
         return _lib
+    if _lib_native is not None and native:
+        return _lib_native
     path = os.path.join(_HERE, "libppo_native.so" if native else "libppo.so")
-    if not os.path.exists(path):
-        build(native)
+    if native or not os.path.exists(path):
+        try:
+            build(native)       # native: re-checks the CPU the file was built on (cheap when up to date)
+        except Exception:
+            if not os.path.exists(path):
+                raise
     L = C.CDLL(path)
     i64, i32, vp = C.c_int64, C.c_int32, C.c_void_p
     L.ppo_query_host.argtypes = [vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp, vp, i64, i64,
@@ -87,7 +117,12 @@ def lib(native: bool = False):
     L.ppo_lower_rank.restype = i64
     L.ppo_extend.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp]
     L.ppo_extend.restype = i64
-    if not native:
+    L.ppo_tuned_available.restype = C.c_int
+    L.ppo_query_host_tuned.argtypes = [vp, i64, vp, i32, i32, i32, vp, i32, vp, i64, i64, vp, vp, i32]
+    L.ppo_query_host_tuned.restype = C.c_int
+    if native:
+        _lib_native = L
+    else:
         _lib = L
     return L
 
@@ -160,6 +195,40 @@ def query(ref, qry, kmers, rand_table=None, ref_cluster=None, qry_cluster=None,
         raise RuntimeError(f"ppo_query_host failed with code {rc}")
     if boundary is not None:
         return out, labels, int(ndeg.value)
+    return out, int(ndeg.value)
+
+
+def tuned_available() -> bool:
+    """The AVX-512 arm (ppb_oracle_tuned.inc) exists only in the -march=native build, on CPUs with VPOPCNTDQ."""
+    try:
+        return bool(lib(native=True).ppo_tuned_available())
+    except Exception:
+        return False
+
+
+def query_tuned(ref, kmers, rand_table=None, ref_cluster=None, row_begin=0, row_end=None, threads=None):
+    """The tuned CPU arm of the self-mode (core, accessory) job: same arithmetic as :func:`query`, bit-identical
+    results, AVX-512 + cache blocking + ln J table (oracle/ppb_oracle_tuned.inc).  Returns ``(out, n_degenerate)``."""
+    L = lib(native=True)
+    ref = np.ascontiguousarray(ref, dtype=np.uint64)
+    n_ref, K, W = ref.shape
+    if W % BBITS:
+        raise ValueError("W must be sketchsize64*14")
+    kmers = np.ascontiguousarray(kmers, dtype=np.int32)
+    nclus = 0
+    if rand_table is not None:
+        rand_table = np.ascontiguousarray(rand_table, dtype=np.float32)
+        nclus = rand_table.shape[0]
+        ref_cluster = np.ascontiguousarray(ref_cluster, dtype=np.uint16)
+    if row_end is None:
+        row_end = num_rows(n_ref)
+    out = np.empty((row_end - row_begin, 2), dtype=np.float32)
+    ndeg = C.c_int64(0)
+    rc = L.ppo_query_host_tuned(_ptr(ref), n_ref, _ptr(kmers), K, W // BBITS, BBITS, _ptr(rand_table), nclus,
+                                _ptr(ref_cluster) if rand_table is not None else None, row_begin, row_end, _ptr(out),
+                                C.byref(ndeg), threads or max_threads())
+    if rc != 0:
+        raise RuntimeError(f"ppo_query_host_tuned failed with code {rc}" + (" (no AVX-512 VPOPCNTDQ)" if rc == 2 else ""))
     return out, int(ndeg.value)
 
 

@@ -130,25 +130,15 @@ static inline double ppo_observed_excess(double obs, double r) {
 /* a6: across-k regression.  Model sketchlib.py:482; clamp = bounds <= 0 at sketchlib.py:660;
  * return order (core, accessory) sketchlib.py:669-670; truncation docs/sketching.rst:161-165.
  * Returns 1 if the pair was degenerate (D3). */
-static inline int ppo_regress(const double *jac, const int32_t *kmers, int K, double S, float *core,
-                              float *acc) {
-    const double tolerance = PPO_MIN_JACCARD_BINS / S;
-    int n = K;
-    for (int t = 0; t < K; t++) {
-        if (jac[t] < tolerance) {
-            n = t;
-            break;
-        }
-    }
+/* the fit itself, on y[t] = ln J_t for the n usable k (shared with the tuned arm, ppb_oracle_tuned.inc) */
+static inline int ppo_fit_logs(const double *y, int n, const int32_t *kmers, float *core, float *acc) {
     if (n < 2) {
         *core = 0.0f;
         *acc = 0.0f;
         return 1;
     }
     double xbar = 0, ybar = 0;
-    double y[PPO_MAX_K];
     for (int t = 0; t < n; t++) {
-        y[t] = log(jac[t]);
         xbar += (double)kmers[t];
         ybar += y[t];
     }
@@ -165,6 +155,21 @@ static inline int ppo_regress(const double *jac, const int32_t *kmers, int K, do
     *core = beta < 0 ? (float)(1.0 - exp(beta)) : 0.0f;
     *acc = alpha < 0 ? (float)(1.0 - exp(alpha)) : 0.0f;
     return 0;
+}
+
+static inline int ppo_regress(const double *jac, const int32_t *kmers, int K, double S, float *core,
+                              float *acc) {
+    const double tolerance = PPO_MIN_JACCARD_BINS / S;
+    int n = K;
+    for (int t = 0; t < K; t++) {
+        if (jac[t] < tolerance) {
+            n = t;
+            break;
+        }
+    }
+    double y[PPO_MAX_K];
+    for (int t = 0; t < n; t++) y[t] = log(jac[t]);
+    return ppo_fit_logs(y, n, kmers, core, acc);
 }
 
 /* Regression only, on caller-supplied per-k Jaccards double [rows][K] (pins a6 against the golden
@@ -689,3 +694,5 @@ int64_t ppo_extend(const int64_t *i_vec, const int64_t *j_vec, const float *d_ve
     free(orr);
     return cnt;
 }
+
+#include "ppb_oracle_tuned.inc"
