@@ -6,6 +6,7 @@
 #   python bench.py ; python bench.py --impl reference --steps 2 --warmup 1 ; python bench.py --config cfg2
 #   nvcc -O2 -std=c++17 -o /tmp/host_floor tools/host_floor.cu -lpthread && /tmp/host_floor 4            # host-side floors
 #   PPB_HOST_TRACE=1 python tools/e2e_dropin.py 100000 1                                                  # first / reuse / steady / np.empty
+#   (kernel variants: at commit bfc6aad — the variant branches were deleted from the source after they were measured)
 #   tools/build_variants.sh dual3:"-DPPB_DUAL_RING=1 -DPPB_STAGES=3" inc:"-DPPB_STAGE_INC=1" \
 #       incprobe:"-DPPB_STAGE_INC=1 -DPPB_EARLY_PROBE=1" defer:"-DPPB_DEFER_PACK=1" all3:"-DPPB_STAGE_INC=1 -DPPB_EARLY_PROBE=1 -DPPB_DEFER_PACK=1"
 #   PPB_LIB=variants/<v>.so python tools/kernel_time.py 100000 [rand]                                     # kernel variants
