@@ -411,6 +411,40 @@ def test_host_pool_without_gpu(lib):
     assert engine.host_result((0, 2), np.float32).shape == (0, 2)
 
 
+def test_visible_devices_knob(monkeypatch):
+    """Which devices a drop-in call uses (engine.visible_devices): all of them with PopPUNK's deviceid leading, or what
+    PPB_DEVICES says — with a stand-in for the library's device count (no GPU here)."""
+    from poppunk_b200 import _lib, engine
+
+    class FakeLib:
+        def __init__(self, n):
+            self.n = n
+
+        def ppb_device_count(self):
+            return self.n
+
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib(8))
+    monkeypatch.delenv("PPB_DEVICES", raising=False)
+    assert engine.visible_devices(0) == list(range(8))
+    assert engine.visible_devices(3) == [3, 0, 1, 2, 4, 5, 6, 7]
+    monkeypatch.setenv("PPB_DEVICES", "single")
+    assert engine.visible_devices(5) == [5]
+    monkeypatch.setenv("PPB_DEVICES", "4")
+    assert engine.visible_devices(6) == [6, 0, 1, 2]
+    monkeypatch.setenv("PPB_DEVICES", "0,2, 7")
+    assert engine.visible_devices(0) == [0, 2, 7]
+    for bad in ("0,0", "1,8", "3,-1"):
+        monkeypatch.setenv("PPB_DEVICES", bad)
+        with pytest.raises(RuntimeError):
+            engine.visible_devices(0)
+    monkeypatch.delenv("PPB_DEVICES")
+    with pytest.raises(RuntimeError):
+        engine.visible_devices(8)                       # PopPUNK's --deviceid beyond the box
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib(0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.visible_devices(0)
+
+
 def test_random_match_fallback_formula():
     """docs/sketching.rst:107-118: r = 1 - (1 - 2 4^-k)^l, J_r = r1 r2 / (r1 + r2 - r1 r2)."""
     from poppunk_b200 import sketchlib
