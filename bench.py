@@ -316,7 +316,20 @@ def capture_traffic(n, timeout_s=240):
                    sys.executable, os.path.abspath(__file__), "--traffic-child", "--genomes", str(n)]
             env = {k: v for k, v in os.environ.items()
                    if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+            # own process group: a timeout must also end the profiled child, not only ncu
+            proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+                                    start_new_session=True)
+            try:
+                _, err = proc.communicate(timeout=timeout_s)
+            except subprocess.TimeoutExpired:
+                import signal
+                try:
+                    os.killpg(proc.pid, signal.SIGKILL)
+                except OSError:
+                    pass
+                proc.communicate()
+                raise
+            res = subprocess.CompletedProcess(cmd, proc.returncode, "", err)
             text = open(logf).read() if os.path.exists(logf) else ""
         rw = parse_ncu_dram_bytes(text)
         if rw is None:
