@@ -23,7 +23,8 @@ Prints ONE JSON line (rank 0).
             bound by the INT32 logic pipe (14 LOP3 per 32 bins), measured here with a LOP3-only micro-kernel, and that
             fraction is the one that says how good the kernel is
   parity    rows sampled from EVERY rank's slice of the timed result, against the CPU oracle and against a single-GPU
-            recompute; the bench exits non-zero on a mismatch
+            recompute; at N=1 also "full_job": EVERY pair of the timed result against the tuned CPU arm of the oracle
+            (about a minute on 16 cores; --full-parity-seconds bounds it); the bench exits non-zero on a mismatch
   cpu_baseline  the CPU oracle (a restatement of the pp-sketchlib CPU path; the library itself is absent) on all host
             cores, on a bounded row range of the same workload; "tuned" inside it = the same arithmetic re-written for
             the host's AVX-512 (oracle/ppb_oracle_tuned.inc, bit-identical results): what the CPU can do
@@ -361,6 +362,36 @@ def run_traffic_child(args):
     torch.cuda.synchronize()
 
 
+def full_parity(out_dev, oracle, ref_np, table, clusters, budget_s, chunk_rows=100_000_000):
+    """EVERY pair of the timed result against the CPU oracle — possible at N=100k because the tuned CPU arm
+    (bit-identical to the restatement, checked above and in tests/) does ~10^8 pairs/s on the host's cores.  Rows are
+    checked in order until the time budget is spent; the line says how far it got."""
+    try:
+        if budget_s <= 0 or not oracle.tuned_available():
+            return None
+        total = out_dev.shape[0]
+        threads = host_threads()
+        t0 = time.perf_counter()
+        rows, worst, n_diff_bits = 0, 0.0, 0
+        while rows < total and time.perf_counter() - t0 < budget_s:
+            r1 = min(total, rows + chunk_rows)
+            got = out_dev[rows:r1].cpu().numpy()
+            exp, _ = oracle.query_tuned(ref_np, KMERS, table, clusters, row_begin=rows, row_end=r1, threads=threads)
+            if not np.array_equal(got.view(np.uint32), exp.view(np.uint32)):
+                n_diff_bits += int((got.view(np.uint32) != exp.view(np.uint32)).any(axis=1).sum())
+                worst = max(worst, float(np.abs(got - exp).max()))
+            rows = r1
+        dt = time.perf_counter() - t0
+        log(f"[bench] full-job parity: rows [0,{rows}) of {total} vs the tuned CPU oracle in {dt:.1f} s: max |d - oracle| = "
+            f"{worst:.2e}, rows not bit-identical: {n_diff_bits}")
+        return {"rows_checked": rows, "rows_total": total, "complete": bool(rows == total), "max_abs_err_vs_oracle": worst,
+                "rows_not_bit_identical": n_diff_bits, "seconds": dt, "ok": bool(worst <= TOL),
+                "checker": "oracle/ppb_oracle_tuned.inc (AVX-512 arm of the CPU oracle, itself bit-identical to the restatement)"}
+    except Exception as ex_:
+        log(f"[bench] full-job parity failed to run: {ex_!r}")
+        return None
+
+
 def sample_ranges(total, world, per_rank=100_000):
     """Row ranges covering the first and the last rows of every rank's slice (shard seams are where bugs live)."""
     from poppunk_b200 import engine
@@ -528,6 +559,7 @@ def run_gpu(args):
         clocks = sampler.stop()
         parity["result"] = check_full(out, packed, "single GPU")
         deg_ranks = degenerate_per_rank(lambda: engine.query(packed, None, KMERS, rand_table=table_dev, out=out, n_degenerate=ndeg))
+        parity["full_job"] = full_parity(out, ora[0], ref_np, table, clusters, args.full_parity_seconds)
         ms_no_table, _ = timed_loop(step_no_table, steps=3, warmup=1)
         mine = out
     else:
@@ -802,6 +834,8 @@ def main():
     ap.add_argument("--config", default="north_star", choices=["north_star", "cfg2", "cfg4", "cfg5"],
                     help="north_star = the driver's bench line; cfg2/cfg4/cfg5 = the other BASELINE.json configs "
                          "(profiles/ lines, see tools/bench_configs.py)")
+    ap.add_argument("--full-parity-seconds", type=float, default=75.0,
+                    help="N=1: time budget for checking EVERY pair of the result against the tuned CPU oracle (0 = skip)")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)   # what capture_traffic() profiles
     args = ap.parse_args()
     if args.traffic_child:
