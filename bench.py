@@ -372,21 +372,31 @@ def full_parity(out_dev, oracle, ref_np, table, clusters, budget_s, chunk_rows=1
         total = out_dev.shape[0]
         threads = host_threads()
         t0 = time.perf_counter()
-        rows, worst, n_diff_bits = 0, 0.0, 0
+        rows, worst, n_diff_bits, sieve_disagrees = 0, 0.0, 0, 0
         while rows < total and time.perf_counter() - t0 < budget_s:
             r1 = min(total, rows + chunk_rows)
             got = out_dev[rows:r1].cpu().numpy()
             exp, _ = oracle.query_tuned(ref_np, KMERS, table, clusters, row_begin=rows, row_end=r1, threads=threads)
             if not np.array_equal(got.view(np.uint32), exp.view(np.uint32)):
-                n_diff_bits += int((got.view(np.uint32) != exp.view(np.uint32)).any(axis=1).sum())
-                worst = max(worst, float(np.abs(got - exp).max()))
+                bad = np.flatnonzero((got.view(np.uint32) != exp.view(np.uint32)).any(axis=1))
+                n_diff_bits += int(bad.size)
+                # the verdict on a differing row is the upstream-shaped restatement's (the tuned arm is only the sieve)
+                order = bad[np.argsort(-np.abs(got[bad] - exp[bad]).max(axis=1))][:64]
+                for r in order:
+                    ref1, _ = oracle.query(ref_np, None, KMERS, table, clusters, row_begin=rows + int(r),
+                                           row_end=rows + int(r) + 1, threads=1)
+                    worst = max(worst, float(np.abs(got[r] - ref1[0]).max()))
+                    if not np.array_equal(ref1[0].view(np.uint32), exp[r].view(np.uint32)):
+                        sieve_disagrees += 1
             rows = r1
         dt = time.perf_counter() - t0
         log(f"[bench] full-job parity: rows [0,{rows}) of {total} vs the tuned CPU oracle in {dt:.1f} s: max |d - oracle| = "
             f"{worst:.2e}, rows not bit-identical: {n_diff_bits}")
         return {"rows_checked": rows, "rows_total": total, "complete": bool(rows == total), "max_abs_err_vs_oracle": worst,
-                "rows_not_bit_identical": n_diff_bits, "seconds": dt, "ok": bool(worst <= TOL),
-                "checker": "oracle/ppb_oracle_tuned.inc (AVX-512 arm of the CPU oracle, itself bit-identical to the restatement)"}
+                "rows_not_bit_identical": n_diff_bits, "tuned_arm_vs_restatement_disagreements": sieve_disagrees,
+                "seconds": dt, "ok": bool(worst <= TOL),
+                "checker": "oracle/ppb_oracle_tuned.inc (AVX-512 arm of the CPU oracle) as the sieve; rows that differ from it "
+                           "(the 64 worst per 1e8-row chunk) are judged against the restatement itself"}
     except Exception as ex_:
         log(f"[bench] full-job parity failed to run: {ex_!r}")
         return None
