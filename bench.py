@@ -788,13 +788,13 @@ def run_gpu(args):
     if world == 1:
         try:
             oracle, native = ora
-            v, cores, rows, _ = cpu_rate(oracle, native, ref_np, table, clusters, 12.0)
+            v, cores, rows, _ = cpu_rate(oracle, native, ref_np, table, clusters, 10.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"rows [0,{rows}) of the same N={n} self job ({rows} pairs)",
                    "note": "CPU restatement of the pp-sketchlib path (oracle/ppb_oracle.c, OpenMP, "
                            + ("-march=native" if native else "-march=x86-64-v3") + "); pp-sketchlib itself is absent; "
                            "parity unpinned"}
-            cpu["tuned"] = cpu_rate_tuned(oracle, ref_np, table, clusters, 6.0)
+            cpu["tuned"] = cpu_rate_tuned(oracle, ref_np, table, clusters, 4.0)
         except Exception as ex_:
             log(f"[bench] cpu baseline failed: {ex_!r}")
 
@@ -844,7 +844,7 @@ def main():
     ap.add_argument("--config", default="north_star", choices=["north_star", "cfg2", "cfg4", "cfg5"],
                     help="north_star = the driver's bench line; cfg2/cfg4/cfg5 = the other BASELINE.json configs "
                          "(profiles/ lines, see tools/bench_configs.py)")
-    ap.add_argument("--full-parity-seconds", type=float, default=75.0,
+    ap.add_argument("--full-parity-seconds", type=float, default=60.0,
                     help="N=1: time budget for checking EVERY pair of the result against the tuned CPU oracle (0 = skip)")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)   # what capture_traffic() profiles
     args = ap.parse_args()
